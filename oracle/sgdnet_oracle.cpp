@@ -23,9 +23,20 @@
  * dense GEMV/.sum() reduction order is implementation-defined; here every reduction is a plain
  * ascending-index sequential sum.
  *
+ * ARITHMETIC MODES (oracle_set_arith / env SGDNET_ORACLE_ARITH):
+ *   1 "portable" (default): inside the solver loop, exp/log are sgd_exp/sgd_log and the dot products / class sums use
+ *      the fixed association order of include/sgdnet_arith.h. This is the arithmetic the GPU library is specified to
+ *      use, so supports, epoch counts and even coefficients can be compared exactly (see the header of
+ *      sgdnet_arith.h for why an exact comparison needs this).
+ *   0 "libm": std::exp/std::log and plain ascending sequential sums - the most literal reading of the reference
+ *      (Eigen's sparse products are sequential; its dense GEMV order is implementation-defined). Used for the CPU
+ *      baseline timings and to bound how much the arithmetic choice matters (tests/test_oracle_cpu.py).
+ * Everything outside the solver loop (setup, deviance, rescale, scoring) is identical in both modes.
+ *
  * Build: g++ -O2 -ffp-contract=off (R's default -O2, no FMA contraction, no -march=native).
  */
 #include "../include/sgdnet_b200.h"
+#include "../include/sgdnet_arith.h"
 
 #include <algorithm>
 #include <chrono>
@@ -39,6 +50,48 @@
 namespace {
 
 thread_local std::string g_err;
+int g_arith = 1;   /* 1 portable, 0 libm */
+
+inline double loop_exp(double x) { return g_arith ? sgd_exp(x) : std::exp(x); }
+inline double loop_log(double x) { return g_arith ? sgd_log(x) : std::log(x); }
+
+/* xor-butterfly 16,8,4,2,1 over 32 slots: the value every lane of a warp ends with after an all-reduce */
+inline double butterfly32(double* v) {
+  double t[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ o];
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+  }
+  return v[0];
+}
+
+/* dense dot product sum_j a[j*sa] * b[j]: 256 interleaved running sums, butterfly per 32, 8 groups ascending */
+inline double dot_dense(const double* a, int64_t sa, const double* b, int64_t p) {
+  if (!g_arith) {
+    double acc = 0.0;
+    for (int64_t j = 0; j < p; ++j) acc += a[j * sa] * b[j];
+    return acc;
+  }
+  double chain[256];
+  for (int i = 0; i < 256; ++i) chain[i] = 0.0;
+  for (int64_t j = 0; j < p; ++j) chain[j & 255] += a[j * sa] * b[j];
+  double total = 0.0;
+  for (int g = 0; g < 8; ++g) total += butterfly32(chain + 32 * g);
+  return total;
+}
+
+/* sparse row dot product sum_e val[e] * w[idx[e]*sw]: 32 interleaved running sums over positions, butterfly */
+inline double dot_sparse(const double* val, const int32_t* idx, int64_t nnz, const double* w, int64_t sw) {
+  if (!g_arith) {
+    double acc = 0.0;
+    for (int64_t e = 0; e < nnz; ++e) acc += val[e] * w[static_cast<size_t>(idx[e]) * sw];
+    return acc;
+  }
+  double chain[32];
+  for (int i = 0; i < 32; ++i) chain[i] = 0.0;
+  for (int64_t e = 0; e < nnz; ++e) chain[e & 31] += val[e] * w[static_cast<size_t>(idx[e]) * sw];
+  return butterfly32(chain);
+}
 
 /* ------------------------------------------------------------------ R-compatible RNG */
 /* R core src/main/RNG.c: MT_sgenrand / MT_genrand, set.seed -> Randomize -> RNG_Init, fixup(). */
@@ -178,15 +231,31 @@ double family_loss(const Model& m, const double* lp, const double* yt, int64_t s
   }
 }
 
+/* LogSumExp inside the solver loop (arithmetic mode aware) */
+double loop_lse(const double* x, int K) {
+  double mx = x[0];
+  for (int k = 1; k < K; ++k) mx = std::max(mx, x[k]);
+  double total;
+  if (g_arith && K <= 32) {
+    double slot[32];
+    for (int k = 0; k < 32; ++k) slot[k] = (k < K) ? loop_exp(x[k] - mx) : 0.0;
+    total = butterfly32(slot);
+  } else {
+    total = 0.0;
+    for (int k = 0; k < K; ++k) total += loop_exp(x[k] - mx);
+  }
+  return loop_log(total) + mx;
+}
+
 void family_gradient(const Model& m, const double* lp, const double* yt, int64_t s, double* g) {
   switch (m.family) {
     case SGDNET_GAUSSIAN: g[0] = lp[0] - yt[s]; break;                                   /* :89-96 */
-    case SGDNET_BINOMIAL: g[0] = 1.0 - yt[s] - 1.0 / (1.0 + std::exp(lp[0])); break;      /* :161-168 */
+    case SGDNET_BINOMIAL: g[0] = 1.0 - yt[s] - 1.0 / (1.0 + loop_exp(lp[0])); break;      /* :161-168 */
     case SGDNET_MULTINOMIAL: {                                                           /* :244-260 */
-      double lse = log_sum_exp(lp, m.K);
+      double lse = loop_lse(lp, m.K);
       unsigned c = static_cast<unsigned>(yt[s] + 0.5);
       for (int k = 0; k < m.K; ++k) {
-        g[k] = std::exp(lp[k] - lse);
+        g[k] = loop_exp(lp[k] - lse);
         if (static_cast<unsigned>(k) == c) g[k] -= 1.0;
       }
       break;
@@ -477,11 +546,7 @@ int saga_dense(const Model& m, const Design& d, const std::vector<double>& c, co
       if (!draw_index(rng, static_cast<uint32_t>(n), &s)) return SGDNET_ERR_RNG;
       const double* xs = &d.dense[static_cast<size_t>(s) * p];
 
-      for (int k = 0; k < K; ++k) lp[k] = 0.0;
-      for (int64_t j = 0; j < p; ++j) {
-        const double* wj = &st.W[static_cast<size_t>(j) * K];
-        for (int k = 0; k < K; ++k) lp[k] += wj[k] * xs[j];
-      }
+      for (int k = 0; k < K; ++k) lp[k] = dot_dense(&st.W[k], K, xs, p);
       for (int k = 0; k < K; ++k) lp[k] = lp[k] * wscale + st.b[k];
 
       family_gradient(m, lp.data(), yt.data(), s, g.data());
@@ -597,16 +662,12 @@ int saga_sparse(const Model& m, const Design& d, const std::vector<double>& c, c
 
       lagged_update(it, s);
 
-      for (int k = 0; k < K; ++k) lp[k] = 0.0;
-      for (int64_t e = d.rp[s]; e < d.rp[s + 1]; ++e) {
-        const double* wj = &st.W[static_cast<size_t>(d.ci[e]) * K];
-        for (int k = 0; k < K; ++k) lp[k] += d.cv[e] * wj[k];
-      }
+      for (int k = 0; k < K; ++k)
+        lp[k] = dot_sparse(&d.cv[d.rp[s]], &d.ci[d.rp[s]], d.rp[s + 1] - d.rp[s], &st.W[k], K);
       for (int k = 0; k < K; ++k) lp[k] = lp[k] * wscale + st.b[k];
       if (stdz) {
         for (int k = 0; k < K; ++k) {
-          double wc = 0.0;
-          for (int64_t j = 0; j < p; ++j) wc += st.W[static_cast<size_t>(j) * K + k] * c[j];
+          double wc = dot_dense(&st.W[k], K, c.data(), p);
           lp[k] -= wc * wscale;
         }
       }
@@ -884,6 +945,11 @@ int fit_path(Design& d /* raw, samples-major */, std::vector<double> y /* n x Ky
 
 bool check_args(int64_t n, int64_t p, const void* y, const sgdnet_control* ctl, const sgdnet_rng* rng,
                 const sgdnet_result* out) {
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    if (const char* e = std::getenv("SGDNET_ORACLE_ARITH")) g_arith = (std::string(e) == "libm" || std::string(e) == "0") ? 0 : 1;
+  }
   if (n <= 0 || p <= 0 || !y || !ctl || !rng || !out) { g_err = "null or empty argument"; return false; }
   if (ctl->family < 0 || ctl->family > 3) { g_err = "unknown family"; return false; }
   if (ctl->n_lambda <= 0 || ctl->n_classes <= 0) { g_err = "n_lambda and n_classes must be positive"; return false; }
@@ -973,6 +1039,9 @@ void colmajor_to_design(const double* x, int64_t n, int64_t p, Design& d) {
 }  // namespace
 
 extern "C" {
+
+void oracle_set_arith(int portable) { g_arith = portable ? 1 : 0; }
+int oracle_get_arith(void) { return g_arith; }
 
 void oracle_rng_set_seed(sgdnet_rng* rng, uint32_t seed) {
   std::memset(rng, 0, sizeof(*rng));

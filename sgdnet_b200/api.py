@@ -350,11 +350,13 @@ def make_foldid(n: int, nfolds: int, perm: np.ndarray) -> np.ndarray:
 def cv_plan(n: int, alphas: Sequence[float], foldid: np.ndarray):
     """The (alpha, fold) work list of R/cv_sgdnet.R:178-200: fold j TRAINS on foldid == j."""
     folds = np.unique(foldid)
+    # one row-id array per fold, shared by every alpha: the backend keys its prepared designs on it
+    split = {int(j): (np.ascontiguousarray(np.nonzero(foldid == j)[0], dtype=np.int32),
+                      np.ascontiguousarray(np.nonzero(foldid != j)[0], dtype=np.int32)) for j in folds}
     plan = []
     for i, a in enumerate(alphas):
         for j in folds:
-            tr = np.nonzero(foldid == j)[0].astype(np.int32)
-            te = np.nonzero(foldid != j)[0].astype(np.int32)
+            tr, te = split[int(j)]
             plan.append(dict(alpha_index=i, alpha=a, fold=int(j), train_rows=tr, test_rows=te))
     return plan
 

@@ -1,0 +1,207 @@
+// common.cuh — device-side vocabulary shared by the sgdnet_b200 kernels (sm_100a, FP64 throughout).
+//
+// The arithmetic below restates, operation for operation, the reference's functors so that the per-element
+// order of floating point operations is the reference's:
+//   SoftThreshold            src/prox.h:32-39
+//   Ridge/ElasticNet/Group   src/penalties.h:27-79
+//   Gradient / Loss          src/families.h:81-96, 152-168, 235-260, 350-365
+//   LogSumExp                src/math.h:25-33
+// The library is compiled with -fmad=false: no multiply-add contraction anywhere. Explicit fma()
+// calls (used only where they are provably exact) are unaffected by that flag.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sgdnet_arith.h"
+
+namespace sgd {
+
+constexpr double kSmall = 100.0 * 2.220446049250313e-16;   // src/constants.h:22
+
+enum Family : int { kGaussian = 0, kBinomial = 1, kMultinomial = 2, kMGaussian = 3 };
+enum Penalty : int { kRidge = 0, kElasticNet = 1, kGroupLasso = 2 };
+enum Status : int { kRunning = 0, kLambdaDone = 1, kFitDone = 2 };
+
+constexpr int kMaxClasses = 64;   // K handled by one warp in the gradient step
+
+// One padded CSR row: `start` is a multiple of 4 entries so that the index run (int32) and the value run (double)
+// both begin on 16-byte boundaries, which is what cp.async.bulk needs. Pad entries are never read as data.
+struct __align__(16) RowInfo {
+  int64_t start;
+  int32_t nnz;
+  int32_t pad_;
+};
+
+// Everything one fit needs on the device. One of these per fit lives in HBM; CTA `blockIdx.x` (or blockIdx.y for
+// the grid-wide passes) works on fit `blockIdx.x`. The host mirrors the struct and re-reads only `Progress`.
+struct FitDev {
+  // ---- problem shape
+  int32_t sparse, family, penalty, fit_intercept;
+  int32_t standardize;       // sparse + standardize: virtual centring through `c` (src/saga-sparse.h:127-128, 276-277)
+  int32_t K, Ky, p, ld;      // ld = dense row stride in doubles (p rounded up to 2)
+  int64_t n;
+  // ---- design (read-only, possibly shared by several fits)
+  const double*  xd;         // dense: [n][ld] row-major, standardised
+  const RowInfo* rows;       // sparse: padded CSR
+  const int32_t* ci;
+  const double*  cv;
+  const double*  c;          // x_center_scaled [p] (zeros unless sparse&&standardize)
+  const double*  yt;         // [n][Ky]
+  // ---- warm-start state (src/sgdnet.cpp:186-198), class-major: W[k*p + j]
+  double *W, *gsum, *Wprev, *b, *gsi, *gmem;   // gmem [n][K]
+  uint32_t* lag;             // [p]
+  double*   lag_scaling;     // [n+1] (unused when ls_identity)
+  // ---- path
+  const double *gamma, *alpha, *beta;   // per lambda
+  int32_t  n_lambda;
+  uint32_t max_iter;
+  double   tol;
+  double   null_deviance_scaled;
+  // ---- rescale inputs and archives (src/utils.h:352-378)
+  const double *x_center, *x_scale, *y_center, *y_scale;
+  double *beta_arch;         // [n_lambda][p][K]
+  double *a0_arch;           // [n_lambda][K]
+  double *dev_ratio;         // [n_lambda]
+  uint32_t *epochs, *codes;  // [n_lambda]
+  double *losses;            // debug: [n_lambda * max_iter] or null
+  // ---- scratch
+  double *partials;          // per-block partial sums for the grid-wide passes
+  int32_t debug;
+  int32_t pad0_;
+};
+
+// Device-updated progress of one fit; read back by the host after every round.
+struct Progress {
+  int32_t  lambda_ind;
+  int32_t  status;           // Status
+  uint32_t it_outer;         // epochs run so far at lambda_ind
+  uint32_t npasses;          // accumulated over the path
+  uint32_t epochs_last_launch;
+  uint32_t pad_;
+  double   wscale;           // carried only inside an epoch; 1.0 between epochs
+};
+
+// ------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ double soft_threshold(double x, double s) {
+  return fmax(x - s, 0.0) - fmax(-x - s, 0.0);
+}
+
+// The three scalars a penalty functor derives from (gamma, beta, w_scale, scaling); computed once per call site with
+// the reference's operation order: step = gamma/w_scale*scaling, thr = beta*gamma*scaling/w_scale (ElasticNet),
+// bgs = beta*gamma*scaling (GroupLasso numerator).
+struct PenCoef {
+  double step, thr, bgs, w_scale;
+};
+__device__ __forceinline__ PenCoef pen_coef(double gamma, double beta, double w_scale, double scaling) {
+  PenCoef c;
+  c.step = gamma / w_scale * scaling;
+  c.bgs = beta * gamma * scaling;
+  c.thr = c.bgs / w_scale;
+  c.w_scale = w_scale;
+  return c;
+}
+
+// penalty(w, j, w_scale, scaling, g_sum) on the K values of one feature, strided by `stride` doubles.
+template <typename WPtr, typename GPtr>
+__device__ __forceinline__ void apply_penalty(int pen, WPtr w, GPtr gs, int K, int stride, const PenCoef& c) {
+  if (pen == kRidge) {
+    for (int k = 0; k < K; ++k) w[k * stride] -= c.step * gs[k * stride];
+  } else if (pen == kElasticNet) {
+    for (int k = 0; k < K; ++k) {
+      double v = w[k * stride] - c.step * gs[k * stride];
+      w[k * stride] = soft_threshold(v, c.thr);
+    }
+  } else {
+    double sq = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double v = w[k * stride] - c.step * gs[k * stride];
+      w[k * stride] = v;
+      sq += v * v;
+    }
+    const double factor = c.bgs / sqrt(sq);
+    if (factor < 1.0) {
+      const double mult = 1.0 - factor / c.w_scale;
+      for (int k = 0; k < K; ++k) w[k * stride] *= mult;
+    } else {
+      for (int k = 0; k < K; ++k) w[k * stride] = 0.0;
+    }
+  }
+}
+
+// K == 1 form used by the hot loops (same operations, no loops)
+__device__ __forceinline__ double penalty_scalar(int pen, double w, double gs, const PenCoef& c) {
+  double v = w - c.step * gs;
+  if (pen == kRidge) return v;
+  if (pen == kElasticNet) return soft_threshold(v, c.thr);
+  const double factor = c.bgs / sqrt(v * v);
+  return (factor < 1.0) ? v * (1.0 - factor / c.w_scale) : 0.0;
+}
+
+// ---- families, scalar (K == 1)
+__device__ __forceinline__ double gradient_scalar(int family, double lp, double y) {
+  if (family == kBinomial) return 1.0 - y - 1.0 / (1.0 + sgd_exp(lp));
+  return lp - y;   // gaussian
+}
+__device__ __forceinline__ double loss_scalar(int family, double lp, double y) {
+  if (family == kBinomial) return sgd_log(1.0 + sgd_exp(lp)) - y * lp;
+  return 0.5 * (lp - y) * (lp - y);
+}
+
+// ---- families, K-vector held one class per lane of a warp (K <= 32 per call chunk is handled by callers through
+// shared memory for larger K). lp/g are per-lane values for class `lane`; lanes >= K pass lp = -inf.
+__device__ __forceinline__ double lse_warp(double lp_lane, bool valid) {
+  double mx = warp_max(valid ? lp_lane : -INFINITY);
+  double e = valid ? sgd_exp(lp_lane - mx) : 0.0;
+  double s = warp_sum(e);          // butterfly over 32 slots padded with zeros (sgdnet_arith.h, item 2)
+  return sgd_log(s) + mx;
+}
+
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// global -> shared bulk copy (UBLKCP in SASS); bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace sgd

@@ -1,0 +1,348 @@
+// passes.cu — the streaming (HBM-bound) passes around the SAGA loop.
+//
+//   lag_scaling_kernel     running geometric sum of src/saga-sparse.h:229-240 (one thread per fit: it is a serial
+//                          floating-point recurrence that must be reproduced in order; rebuilt at every lambda)
+//   loss_pass_kernel       per-lambda Deviance (src/utils.h:304-329) and the debug EpochLoss (src/utils.h:199-227):
+//                          one warp per sample, X streamed once, block partial sums, fixed-order final sum
+//   finish_lambda_kernel   dev.ratio (src/sgdnet.cpp:246-258), Rescale + archive (src/utils.h:352-378), and the
+//                          per-fit state machine step to the next lambda
+//   predict / score        X * [a0; beta] for all lambda at once (R/predict.sgdnet.R:377, 507-510) and the held-out
+//                          deviance of R/score.R:55-178, lanes across lambda so the coefficient reads are coalesced
+//
+// Algorithmic HBM bytes per loss pass: sparse 12*nnz + 16*n (row info) + 8*n*K_y; dense 8*n*ld + 8*n*K_y.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sgd {
+
+constexpr int kPassThreads = 256;
+
+// ------------------------------------------------------------------------------------------ lag scaling
+__global__ void lag_scaling_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog) {
+  const int fit_id = blockIdx.x;
+  const Progress& pg = prog[fit_id];
+  if (pg.status != kRunning || pg.it_outer != 0) return;
+  const FitDev& f = fits[fit_id];
+  if (!f.sparse || threadIdx.x != 0) return;
+  const int li = pg.lambda_ind;
+  const double r = 1.0 - f.alpha[li] * f.gamma[li];
+  if (r == 1.0) return;   // table would hold exact integers; the solver uses (double)m directly
+  double* __restrict__ ls = f.lag_scaling;
+  ls[0] = 0.0;
+  ls[1] = 1.0;
+  double geo = 1.0, last = 1.0;
+  const uint32_t n1 = static_cast<uint32_t>(f.n) + 1u;
+  for (uint32_t i = 2; i < n1; ++i) {
+    geo *= r;
+    last = last + geo;
+    ls[i] = last;
+  }
+}
+
+cudaError_t launch_lag_scaling(int n_fits, FitDev* fits, Progress* prog, cudaStream_t st) {
+  lag_scaling_kernel<<<n_fits, 32, 0, st>>>(fits, prog);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ loss pass
+// mode 0: deviance for fits with status == kLambdaDone; mode 1: epoch loss (debug) for fits that just ran an epoch.
+__device__ __forceinline__ double sample_loss_warp(const FitDev& f, int K, int Ky, double lp_lane, int64_t s, int lane) {
+  // lanes 0..K-1 hold lp[k]; returns the loss in every lane
+  if (K == 1) {
+    const double y = f.yt[s];
+    return loss_scalar(f.family, __shfl_sync(0xffffffffu, lp_lane, 0), y);
+  }
+  const bool valid = lane < K;
+  if (f.family == kMultinomial) {
+    const double lse = lse_warp(lp_lane, valid);
+    const unsigned c = static_cast<unsigned>(f.yt[s] + 0.5);
+    const double lpc = __shfl_sync(0xffffffffu, lp_lane, static_cast<int>(c));
+    return lse - lpc;
+  }
+  double d = 0.0;
+  if (valid) {
+    d = lp_lane - f.yt[s * Ky + lane];
+    d = d * d;
+  }
+  return 0.5 * warp_sum(d);
+}
+
+__global__ void __launch_bounds__(kPassThreads)
+loss_pass_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
+                 int mode) {
+  __shared__ double wc_s[32];
+  __shared__ double red_s[kPassThreads / 32];
+  __shared__ double red2[2 * (kPassThreads / 32) * 32];
+  const int fit_id = blockIdx.y;
+  const Progress& pg = prog[fit_id];
+  const FitDev& f = fits[fit_id];
+  if (mode == 0 ? (pg.status != kLambdaDone) : (args[fit_id].n_epochs == 0 || !f.debug)) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int K = f.K, Ky = f.Ky, p = f.p, ld = f.ld;
+  const int64_t n = f.n;
+  const double* __restrict__ W = f.W;
+  const bool stdz = f.sparse && f.standardize;
+
+  // W . c per class (virtual centring), once per block
+  if (stdz) {
+    for (int k = 0; k < K; ++k) {
+      double a = 0.0;
+      for (int j = tid; j < p; j += blockDim.x) a += W[size_t(k) * p + j] * f.c[j];
+      a = warp_sum(a);
+      if (lane == 0) red2[warp * 32 + k] = a;
+    }
+    __syncthreads();
+    if (tid < K) {
+      double a = 0.0;
+      for (int w = 0; w < nwarps; ++w) a += red2[w * 32 + tid];
+      wc_s[tid] = a;
+    }
+    __syncthreads();
+  }
+
+  const double bk = (lane < K) ? f.b[lane] : 0.0;
+  double acc = 0.0;
+  const int64_t warp_global = int64_t(blockIdx.x) * nwarps + warp;
+  const int64_t warp_stride = int64_t(gridDim.x) * nwarps;
+  for (int64_t s = warp_global; s < n; s += warp_stride) {
+    double lp_lane = 0.0;
+    if (f.sparse) {
+      const RowInfo ri = f.rows[s];
+      const int32_t* __restrict__ ci = f.ci + ri.start;
+      const double* __restrict__ cv = f.cv + ri.start;
+      for (int k = 0; k < K; ++k) {
+        double a = 0.0;
+        for (int e = lane; e < ri.nnz; e += 32) a += cv[e] * W[size_t(k) * p + ci[e]];
+        a = warp_sum(a);
+        if (lane == k) lp_lane = a;
+      }
+    } else {
+      const double* __restrict__ xr = f.xd + size_t(s) * ld;
+      for (int k = 0; k < K; ++k) {
+        double a = 0.0;
+        for (int j = lane; j < p; j += 32) a += W[size_t(k) * p + j] * xr[j];
+        a = warp_sum(a);
+        if (lane == k) lp_lane = a;
+      }
+    }
+    if (lane < K) {
+      lp_lane += bk;
+      if (stdz) lp_lane -= wc_s[lane];
+    }
+    double loss = sample_loss_warp(f, K, Ky, lp_lane, s, lane);
+    if (mode == 1) loss = loss / static_cast<double>(static_cast<uint32_t>(n));
+    acc += loss;
+  }
+  if (lane == 0) red_s[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int w = 0; w < nwarps; ++w) a += red_s[w];
+    f.partials[blockIdx.x] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ finish lambda
+__global__ void __launch_bounds__(kPassThreads)
+finish_lambda_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, int n_partials) {
+  __shared__ double red[(kPassThreads / 32) * 32];
+  __shared__ double xbs[32];
+  const int fit_id = blockIdx.x;
+  Progress& pg = prog[fit_id];
+  if (pg.status != kLambdaDone) return;
+  const FitDev& f = fits[fit_id];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int K = f.K, p = f.p;
+  const int li = pg.lambda_ind;
+
+  // Rescale (src/utils.h:363-377): beta_j = w_j * y_scale / x_scale_j ; a0 = b*y_scale + y_center - sum_j x_center_j beta_j
+  double* __restrict__ ba = f.beta_arch + size_t(li) * p * K;
+  for (int k = 0; k < K; ++k) {
+    double a = 0.0;
+    const double ys = f.y_scale[k];
+    for (int j = tid; j < p; j += blockDim.x) {
+      const double v = f.W[size_t(k) * p + j] * (ys / f.x_scale[j]);
+      ba[size_t(j) * K + k] = v;
+      a += f.x_center[j] * v;
+    }
+    a = warp_sum(a);
+    if (lane == 0) red[warp * 32 + k] = a;
+  }
+  __syncthreads();
+  if (tid < K) {
+    double a = 0.0;
+    for (int w = 0; w < nwarps; ++w) a += red[w * 32 + tid];
+    xbs[tid] = a;
+    double b = f.b[tid];
+    if (f.fit_intercept) b = b * f.y_scale[tid] + f.y_center[tid] - a;
+    f.a0_arch[size_t(li) * K + tid] = b;
+  }
+  if (tid == 0) {
+    double dev = 0.0;
+    for (int i = 0; i < n_partials; ++i) dev += f.partials[i];
+    dev = 2.0 * dev;
+    f.dev_ratio[li] = 1.0 - dev / f.null_deviance_scaled;
+    pg.lambda_ind = li + 1;
+    pg.it_outer = 0;
+    pg.status = (li + 1 >= f.n_lambda) ? kFitDone : kRunning;
+  }
+}
+
+cudaError_t launch_finish_lambda(int n_fits, FitDev* fits, Progress* prog, int blocks_per_fit, cudaStream_t st) {
+  dim3 grid(blocks_per_fit, n_fits);
+  loss_pass_kernel<<<grid, kPassThreads, 0, st>>>(fits, prog, nullptr, 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  finish_lambda_kernel<<<n_fits, kPassThreads, 0, st>>>(fits, prog, blocks_per_fit);
+  return cudaGetLastError();
+}
+
+// debug: per-epoch mean loss appended to f.losses[lambda_ind * max_iter + it_outer - 1]
+__global__ void store_epoch_loss_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog,
+                                        const RoundArgs* __restrict__ args, int n_partials) {
+  const int fit_id = blockIdx.x;
+  const Progress& pg = prog[fit_id];
+  const FitDev& f = fits[fit_id];
+  if (args[fit_id].n_epochs == 0 || !f.debug || threadIdx.x != 0) return;
+  double loss = 0.0;
+  for (int i = 0; i < n_partials; ++i) loss += f.partials[i];
+  // after an epoch the fit is either still running at lambda_ind, or it just finished lambda_ind (status LambdaDone)
+  f.losses[size_t(pg.lambda_ind) * f.max_iter + (pg.it_outer - 1)] = loss;
+}
+
+cudaError_t launch_epoch_loss(int n_fits, FitDev* fits, Progress* prog, const RoundArgs* args, int blocks_per_fit,
+                              cudaStream_t st) {
+  dim3 grid(blocks_per_fit, n_fits);
+  loss_pass_kernel<<<grid, kPassThreads, 0, st>>>(fits, prog, args, 1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  store_epoch_loss_kernel<<<n_fits, 32, 0, st>>>(fits, prog, args, blocks_per_fit);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ predict / score
+// Bt[j][l*K + k] = beta[l][j][k]: coefficient rows contiguous across lambda for coalesced SpMM reads.
+__global__ void transpose_beta_kernel(const double* __restrict__ beta, double* __restrict__ bt, int L, int p, int K) {
+  const size_t total = size_t(L) * p * K;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const size_t jl = i / K;
+    const int j = static_cast<int>(jl % p);
+    const int l = static_cast<int>(jl / p);
+    bt[size_t(j) * L * K + size_t(l) * K + k] = beta[i];
+  }
+}
+
+// One warp per row; lanes across lambda (chunks of 32). For each class k the row is re-walked (it sits in L1).
+__global__ void __launch_bounds__(kPassThreads)
+predict_score_kernel(PredictArgs a, const double* __restrict__ bt) {
+  extern __shared__ double acc_s[];   // [nwarps][L]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int L = a.n_lambda, K = a.K, Ky = a.Ky, p = a.p;
+  const int LK = L * K;
+  double* my_acc = acc_s + size_t(warp) * L;
+  for (int l = lane; l < L; l += 32) my_acc[l] = 0.0;
+  __syncwarp();
+  const double pmin = 1e-5, pmax = 1.0 - 1e-5;
+
+  const int64_t warp_global = int64_t(blockIdx.x) * nwarps + warp;
+  const int64_t warp_stride = int64_t(gridDim.x) * nwarps;
+  for (int64_t i = warp_global; i < a.n; i += warp_stride) {
+    const int64_t s = a.row_ids ? a.row_ids[i] : i;
+    int nnz;
+    const int32_t* ci = nullptr;
+    const double* cv = nullptr;
+    const double* xr = nullptr;
+    if (a.sparse) {
+      const RowInfo ri = a.rows[s];
+      nnz = ri.nnz;
+      ci = a.ci + ri.start;
+      cv = a.cv + ri.start;
+    } else {
+      nnz = p;
+      xr = a.xd + size_t(s) * a.ld;
+    }
+    for (int l0 = 0; l0 < L; l0 += 32) {
+      const int l = l0 + lane;
+      const bool valid = l < L;
+      double tot = 0.0, lp_true = 0.0, sq = 0.0, lp0 = 0.0;
+      unsigned cls = 0;
+      if (a.y && (a.family == kMultinomial)) cls = static_cast<unsigned>(a.y[s * Ky] + 0.5);
+      for (int k = 0; k < K; ++k) {
+        double lp = valid ? a.a0[size_t(l) * K + k] : 0.0;
+        if (valid) {
+          const double* __restrict__ col = bt + size_t(l) * K + k;
+          if (a.sparse) {
+            for (int e = 0; e < nnz; ++e) lp += cv[e] * col[size_t(ci[e]) * LK];
+          } else {
+            for (int j = 0; j < p; ++j) lp += xr[j] * col[size_t(j) * LK];
+          }
+          if (a.link) a.link[(size_t(l) * K + k) * a.n + i] = lp;
+          if (a.y) {
+            if (a.family == kMultinomial) {
+              tot += sgd_exp(lp);
+              if (static_cast<unsigned>(k) == cls) lp_true = lp;
+            } else if (a.family == kMGaussian) {
+              const double rr = lp - a.y[s * Ky + k];
+              sq += rr * rr;
+            } else {
+              lp0 = lp;
+            }
+          }
+        }
+      }
+      if (valid && a.y) {
+        double contrib;
+        if (a.family == kGaussian) {
+          const double rr = lp0 - a.y[s];
+          contrib = rr * rr;
+        } else if (a.family == kBinomial) {
+          double pr = 1.0 / (1.0 + sgd_exp(-lp0));
+          pr = fmin(fmax(pr, pmin), pmax);
+          contrib = 2.0 * (0.0 - ((a.y[s] > 0.5) ? sgd_log(pr) : sgd_log(1.0 - pr)));
+        } else if (a.family == kMultinomial) {
+          double pr = sgd_exp(lp_true) / tot;
+          pr = fmin(fmax(pr, pmin), pmax);
+          contrib = 2.0 * (0.0 - sgd_log(pr));
+        } else {
+          contrib = sq;
+        }
+        my_acc[l] += contrib;
+      }
+    }
+  }
+  __syncthreads();
+  if (a.partials) {
+    for (int l = tid; l < L; l += blockDim.x) {
+      double t = 0.0;
+      for (int w = 0; w < nwarps; ++w) t += acc_s[size_t(w) * L + l];
+      a.partials[size_t(blockIdx.x) * L + l] = t;
+    }
+  }
+}
+
+__global__ void score_finalize_kernel(PredictArgs a, int blocks) {
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_lambda; l += gridDim.x * blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < blocks; ++b) t += a.partials[size_t(b) * a.n_lambda + l];
+    a.score[l] = (a.family == kMGaussian) ? t / a.K : t / static_cast<double>(a.n);
+  }
+}
+
+cudaError_t launch_predict_score(const PredictArgs& a, double* bt_scratch, int blocks, cudaStream_t st) {
+  transpose_beta_kernel<<<296, 256, 0, st>>>(a.beta, bt_scratch, a.n_lambda, a.p, a.K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t smem = sizeof(double) * (kPassThreads / 32) * a.n_lambda;
+  predict_score_kernel<<<blocks, kPassThreads, smem, st>>>(a, bt_scratch);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (a.score) {
+    score_finalize_kernel<<<1, 128, 0, st>>>(a, blocks);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace sgd

@@ -1,0 +1,54 @@
+"""include/sgdnet_arith.h: the specified exp/log are faithful (< 1 ulp against 200-bit references) and handle the
+IEEE special cases."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def arith():
+    src = '#include "include/sgdnet_arith.h"\nextern "C" double t_exp(double x){return sgd_exp(x);}\nextern "C" double t_log(double x){return sgd_log(x);}\n'
+    so = os.path.join(ROOT, "build", "arith_test.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-", "-I", ROOT, "-o", so],
+                   input=src.encode(), cwd=ROOT, check=True)
+    lib = C.CDLL(so)
+    for f in (lib.t_exp, lib.t_log):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    return lib
+
+
+def ulp_error(got, ref_mp):
+    import mpmath as mp
+    r = float(ref_mp)
+    return abs(float((mp.mpf(got) - ref_mp) / mp.mpf(float(np.spacing(abs(r))))))
+
+
+def test_exp_is_faithful(arith):
+    import mpmath as mp
+    mp.mp.prec = 200
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-40, 40, 4000), rng.uniform(-745, 709.7, 1500), rng.uniform(-1e-3, 1e-3, 500),
+                         [0.0, 1.0, -1.0, 709.782712893384, -745.13, -708.4, -740.0]])
+    worst = max(ulp_error(arith.t_exp(float(x)), mp.exp(mp.mpf(float(x)))) for x in xs)
+    assert worst < 1.0
+    assert arith.t_exp(0.0) == 1.0 and arith.t_exp(710.0) == np.inf and arith.t_exp(-746.0) == 0.0
+    assert np.isnan(arith.t_exp(float("nan")))
+
+
+def test_log_is_faithful(arith):
+    import mpmath as mp
+    mp.mp.prec = 200
+    rng = np.random.default_rng(1)
+    ys = np.concatenate([np.exp(rng.uniform(-700, 700, 3000)), rng.uniform(0.5, 2.0, 3000), rng.uniform(0.99, 1.01, 1000),
+                         [2.0, 0.5, 5e-324, 1e-310, 1.7976931348623157e308]])
+    worst = max(ulp_error(arith.t_log(float(y)), mp.log(mp.mpf(float(y)))) for y in ys)
+    assert worst < 1.0
+    assert arith.t_log(1.0) == 0.0 and arith.t_log(0.0) == -np.inf and arith.t_log(np.inf) == np.inf
+    assert np.isnan(arith.t_log(-1.0))

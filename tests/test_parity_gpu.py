@@ -1,0 +1,145 @@
+"""GPU parity tests proper: every call goes through the C ABI of libsgdnet_b200.so and is compared with the CPU
+oracle on the same seeded inputs and the same R-compatible sampling sequence."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sgdnet_b200 as sg
+from conftest import golden
+from parity import assert_fit_parity, rel_close
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def both(cuda, oracle, x, y, **kw):
+    g = sg.sgdnet(x, y, backend=cuda, **kw)
+    r = sg.sgdnet(x, y, backend=oracle, **kw)
+    return g, r
+
+
+def test_c1_abalone_gaussian_elasticnet(cuda, oracle):
+    """BASELINE config 1: gaussian, alpha = 0.5, 100-lambda path on the bundled abalone data, set.seed(1)."""
+    d = golden("abalone")
+    g, r = both(cuda, oracle, d["x"], d["y"], family="gaussian", alpha=0.5, seed=1)
+    assert r.npasses == 1143            # pinned by the survey's independent restatement
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("intercept", [True, False])
+@pytest.mark.parametrize("standardize", [True, False])
+def test_dense_binomial_grid(cuda, oracle, alpha, intercept, standardize):
+    x, y = synth.random_data(300, 5, "binomial", intercept, density=0.8, seed=11)
+    g, r = both(cuda, oracle, x.toarray(), y, family="binomial", alpha=alpha, intercept=intercept,
+                standardize=standardize, nlambda=12, thresh=1e-4, maxit=300, seed=3)
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.8, 1.0])
+def test_dense_multinomial_wine(cuda, oracle, alpha):
+    d = golden("wine")
+    g, r = both(cuda, oracle, d["x"], d["y"], family="multinomial", alpha=alpha, nlambda=15, seed=2)
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("alpha", [0.0, 1.0])
+@pytest.mark.parametrize("standardize_response", [False, True])
+def test_dense_mgaussian_student(cuda, oracle, alpha, standardize_response):
+    d = golden("student")
+    g, r = both(cuda, oracle, d["x"], d["y"], family="mgaussian", alpha=alpha, nlambda=15,
+                standardize_response=standardize_response, seed=4)
+    assert_fit_parity(g.raw, r.raw)
+
+
+def _heart():
+    d = golden("heart")
+    n, p = (int(v) for v in d["x_shape"])
+    return sp.csc_matrix((d["x_x"], d["x_i"], d["x_p"]), shape=(n, p)), d["y"]
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_sparse_binomial_heart(cuda, oracle, alpha, standardize):
+    x, y = _heart()
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=alpha, standardize=standardize, nlambda=12,
+                maxit=200, seed=5)
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("family", ["gaussian", "binomial"])
+@pytest.mark.parametrize("alpha", [0.0, 0.3, 1.0])
+@pytest.mark.parametrize("intercept", [True, False])
+def test_sparse_k1_synthetic(cuda, oracle, family, alpha, intercept):
+    """Genuinely sparse rows (the lagged path the reference's own tests never reach)."""
+    x, yb = synth.binomial_sparse(2000, 400, 12, seed=21)
+    y = yb if family == "binomial" else (x @ np.linspace(-1, 1, 400) + 0.1 * yb)
+    g, r = both(cuda, oracle, x, y, family=family, alpha=alpha, intercept=intercept, standardize=False,
+                nlambda=10, thresh=1e-4, maxit=100, seed=6)
+    assert_fit_parity(g.raw, r.raw)
+
+
+def test_sparse_long_and_empty_rows(cuda, oracle):
+    """Rows longer than a ring slot (> 128 nonzeros) and empty rows take the in-place path."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = sp.random(400, 600, density=0.3, random_state=7, format="lil")
+    x[3, :] = 0
+    x[17, :] = 0
+    x[5, :] = rng.uniform(0.1, 1.0, size=600)     # one fully dense row
+    x = sp.csc_matrix(x)
+    y = (rng.uniform(size=400) < 0.5).astype(float)
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=0.9, standardize=False, nlambda=6, maxit=50, seed=8)
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("family", ["multinomial", "mgaussian"])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_sparse_generic_multiclass(cuda, oracle, family, standardize):
+    x, y = synth.random_data(250, 6, family, True, density=0.4, seed=13)
+    g, r = both(cuda, oracle, x, y, family=family, alpha=0.7, standardize=standardize, nlambda=8, maxit=150, seed=9)
+    assert_fit_parity(g.raw, r.raw)
+
+
+def test_user_lambda_order_and_debug_losses(cuda, oracle):
+    d = golden("abalone")
+    lam = [0.5, 2.0, 0.01]           # unsorted: used in the given order (quirk Q14)
+    g, r = both(cuda, oracle, d["x"][:800], d["y"][:800], family="gaussian", alpha=0.3, lambda_=lam, seed=10,
+                debug=True)
+    assert_fit_parity(g.raw, r.raw)
+    for lg, lr in zip(g.diagnostics["loss"], r.diagnostics["loss"]):
+        rel_close(lg, lr, what="debug losses")
+
+
+def test_rng_stream_is_advanced_exactly(cuda, oracle):
+    """The generator handed back has consumed n * npasses draws: a second fit continues the same stream."""
+    x, y = synth.random_data(200, 4, "gaussian", True, density=1.0, seed=3)
+    x = x.toarray()
+    rg, ro = cuda.rng_from_seed(99), oracle.rng_from_seed(99)
+    g1 = sg.sgdnet(x, y, nlambda=5, rng=rg, backend=cuda)
+    r1 = sg.sgdnet(x, y, nlambda=5, rng=ro, backend=oracle)
+    assert g1.npasses == r1.npasses
+    np.testing.assert_array_equal(cuda.unif(rg, 5), oracle.unif(ro, 5))
+
+
+def test_predict_and_score(cuda, oracle):
+    x, y = _heart()
+    fit = sg.sgdnet(x, y, family="binomial", alpha=0.5, standardize=False, nlambda=10, seed=1, backend=cuda)
+    a0 = fit.raw.a0
+    beta = fit.raw.beta
+    rel_close(cuda.predict(x, a0, beta), oracle.predict(x, a0, beta), rtol=1e-12, what="link")
+    rel_close(cuda.predict(x.toarray(), a0, beta), oracle.predict(x.toarray(), a0, beta), rtol=1e-12, what="link dense")
+    yy = (y == y.max()).astype(float)
+    rel_close(cuda.score_deviance(x, yy, 1, a0, beta), oracle.score_deviance(x, yy, 1, a0, beta), rtol=1e-10, what="score")
+
+
+def test_cv_batch_matches_sequential_oracle(cuda, oracle):
+    x, y = synth.binomial_sparse(1500, 300, 10, seed=31)
+    foldid = (np.random.Generator(np.random.PCG64(1)).permutation(1500) % 5) + 1
+    kw = dict(family="binomial", alpha=[0.0, 0.5, 1.0], foldid=foldid, nlambda=8, standardize=False, maxit=100, seed=1000)
+    g = sg.cv_sgdnet(x, y, backend=cuda, **kw)
+    r = sg.cv_sgdnet(x, y, backend=oracle, batched=False, **kw)
+    for fg, fr in zip(g.fold_fits, r.fold_fits):
+        assert_fit_parity(fg.raw, fr.raw)
+    for cg, cr in zip(g.cv_raw, r.cv_raw):
+        rel_close(cg, cr, what="cv_raw")
+    assert g.alpha_min == r.alpha_min and g.lambda_min == r.lambda_min and g.lambda_1se == r.lambda_1se
