@@ -140,31 +140,60 @@ saga_sparse_k1_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, co
     const uint32_t* __restrict__ eseq = seq + size_t(ep) * n;
 
     if (warp == 1) {
-      // ------------------------------------------------------------------ producer: lane l feeds slot l
-      if (lane < kSlots) {
-        // rows whose ring sequence number q = q_base + t falls on this lane's slot
-        for (int64_t t = (lane - static_cast<int>(q_base % kSlots) + kSlots) % kSlots; t < n; t += kSlots) {
-          const int64_t q = q_base + t;
-          const uint32_t s = eseq[t];
-          const RowInfo ri = f.rows[s];
-          const double y = f.yt[s];
-          mbar_wait(&ring.empty[lane], static_cast<uint32_t>(((q / kSlots) & 1) ^ 1));
-          SpSlotMeta m;
-          m.s = s;
-          m.nnz = ri.nnz;
-          m.start = ri.start;
-          m.y = y;
-          ring.meta[lane] = m;
-          if (ri.nnz > 0 && ri.nnz <= kCap) {
-            const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
-            const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
-            mbar_expect_tx(&ring.full[lane], bi + bv);
-            bulk_g2s(ring.idx[lane], f.ci + ri.start, bi, &ring.full[lane]);
-            bulk_g2s(ring.val[lane], f.cv + ri.start, bv, &ring.full[lane]);
-          } else {
-            mbar_arrive(&ring.full[lane]);
+      // ------------------------------------------------------------------ producer: lane l feeds ring slot l
+      // Warp-synchronous: the 16 lanes load the sample index, row descriptor and response of their next row together
+      // (16 independent HBM requests in flight), one batch ahead of the batch being issued, then the warp polls the
+      // slots' "empty" barriers and issues each row's two bulk copies as soon as its slot is released.
+      const bool feeder = lane < kSlots;
+      int64_t t = (lane - static_cast<int>(q_base % kSlots) + kSlots) % kSlots;   // q = q_base + t lands on slot `lane`
+      bool have = feeder && t < n;
+      uint32_t s = 0;
+      RowInfo ri{};
+      double y = 0.0;
+      if (have) {
+        s = eseq[t];
+        ri = f.rows[s];
+        y = f.yt[s];
+      }
+      while (__any_sync(0xffffffffu, have)) {
+        const int64_t tn = t + kSlots;
+        const bool have_n = feeder && tn < n;
+        uint32_t sn = 0;
+        RowInfo rin{};
+        double yn = 0.0;
+        if (have_n) {
+          sn = eseq[tn];
+          rin = f.rows[sn];
+          yn = f.yt[sn];
+        }
+        bool pending = have;
+        const int64_t q = q_base + t;
+        const uint32_t par = static_cast<uint32_t>(((q / kSlots) & 1) ^ 1);
+        while (__any_sync(0xffffffffu, pending)) {
+          if (pending && mbar_try_wait(&ring.empty[lane], par)) {
+            SpSlotMeta m;
+            m.s = s;
+            m.nnz = ri.nnz;
+            m.start = ri.start;
+            m.y = y;
+            ring.meta[lane] = m;
+            if (ri.nnz > 0 && ri.nnz <= kCap) {
+              const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
+              const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
+              mbar_expect_tx(&ring.full[lane], bi + bv);
+              bulk_g2s(ring.idx[lane], f.ci + ri.start, bi, &ring.full[lane]);
+              bulk_g2s(ring.val[lane], f.cv + ri.start, bv, &ring.full[lane]);
+            } else {
+              mbar_arrive(&ring.full[lane]);
+            }
+            pending = false;
           }
         }
+        t = tn;
+        have = have_n;
+        s = sn;
+        ri = rin;
+        y = yn;
       }
     } else if (warp == 0) {
       // ------------------------------------------------------------------ solver warp
