@@ -33,6 +33,14 @@ struct __align__(16) RowInfo {
   int32_t pad_;
 };
 
+// Sparse K == 1 coefficient state, one 32-byte record per feature so that a row's gather / scatter is a single
+// 256-bit access per nonzero (saga_sparse.cu, wavefront kernel).
+struct __align__(32) FeatState {
+  double w, g;
+  uint32_t lag, pad0_;
+  uint64_t pad1_;
+};
+
 // Everything one fit needs on the device. One of these per fit lives in HBM; CTA `blockIdx.x` (or blockIdx.y for
 // the grid-wide passes) works on fit `blockIdx.x`. The host mirrors the struct and re-reads only `Progress`.
 struct FitDev {
@@ -51,6 +59,7 @@ struct FitDev {
   // ---- warm-start state (src/sgdnet.cpp:186-198), class-major: W[k*p + j]
   double *W, *gsum, *Wprev, *b, *gsi, *gmem;   // gmem [n][K]
   uint32_t* lag;             // [p]
+  FeatState* st;             // [p] sparse K == 1: packed {W, gsum, lag} (then W mirrors st.w at epoch ends only)
   double*   lag_scaling;     // [n+1] (unused when ls_identity)
   // ---- path
   const double *gamma, *alpha, *beta;   // per lambda

@@ -98,6 +98,8 @@ struct FitJob {
   uint64_t generated = 0;
   uint32_t* seq_dev = nullptr;
   uint32_t* seq_pin = nullptr;
+  uint16_t* dep_dev = nullptr;        // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
+  uint8_t* dup_dev = nullptr;
   int epochs_per_launch = 1;
   bool done = false;
   // scoring of held-out rows after the fit (cv)
@@ -122,6 +124,8 @@ struct Engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   int loss_blocks = 1;
+  int sms = 148;
+  int64_t max_rows_per_launch = 1;
   size_t dense_smem = 0;
   Variant variant = Variant::Dense;
   bool any_debug = false;
@@ -222,6 +226,7 @@ struct Engine {
     f.gsi = arena.alloc<double>(K);
     f.gmem = arena.alloc<double>(size_t(d.n) * K);
     f.lag = arena.alloc<uint32_t>(p);
+    f.st = (d.sparse && K == 1 && !f.standardize) ? arena.alloc<FeatState>(p) : nullptr;
     f.lag_scaling = d.sparse ? arena.alloc<double>(size_t(d.n) + 1, false) : nullptr;
     f.gamma = arena.upload(pl.gamma);
     f.alpha = arena.upload(pl.alpha);
@@ -252,6 +257,10 @@ struct Engine {
     job.epochs_per_launch = epl;
     job.seq_dev = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
     job.seq_pin = arena.host<uint32_t>(size_t(epl) * d.n);
+    if (d.sparse && K == 1 && !f.standardize) {
+      job.dep_dev = arena.alloc<uint16_t>(size_t(epl) * d.n * 32, false);
+      job.dup_dev = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
+    }
     jobs.push_back(std::move(job));
     return "";
   }
@@ -275,8 +284,10 @@ struct Engine {
       dense_smem = dense_smem_bytes(max_K, max_p, max_ld, &in_smem);
     }
     // streaming passes: enough CTAs to fill the GPU across the fits of the batch, at least one per fit
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    for (auto& j : jobs) max_rows_per_launch = std::max<int64_t>(max_rows_per_launch, j.dev.n * j.epochs_per_launch);
     const int64_t want = std::max<int64_t>(1, (int64_t(sms) * 4 + nf - 1) / nf);
     loss_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (max_n + 7) / 8)));
     for (auto& j : jobs) j.dev.partials = arena.alloc<double>(loss_blocks);
@@ -346,7 +357,7 @@ struct Engine {
         const Progress& pg = prog_host[i];
         const bool stop_here = (only_lambda >= 0 && pg.lambda_ind > only_lambda);
         if (j.done || pg.status == kFitDone || stop_here) {
-          args_host[i] = RoundArgs{nullptr, 0, 0};
+          args_host[i] = RoundArgs{nullptr, nullptr, nullptr, 0, 0};
           continue;
         }
         const uint32_t left = j.plan.max_iter - pg.it_outer;
@@ -356,7 +367,7 @@ struct Engine {
           throw CudaFail{cudaSuccess, "rng"};
         }
         CK(cudaMemcpyAsync(j.seq_dev, j.seq_pin, size_t(ne) * j.dev.n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        args_host[i] = RoundArgs{j.seq_dev, ne, 0};
+        args_host[i] = RoundArgs{j.seq_dev, j.dep_dev, j.dup_dev, ne, 0};
         ++active;
       }
       if (active == 0) break;
@@ -366,6 +377,10 @@ struct Engine {
         ++launches;
       }
       CK(cudaEventRecord(ev0, stream));
+      if (variant == Variant::SparseK1) {
+        CK(launch_wave_deps(nf, fits_dev, prog_dev, args_dev, max_rows_per_launch, sms, stream));
+        ++launches;
+      }
       if (variant == Variant::Dense)
         CK(launch_saga_dense(nf, jobs[0].dev.K == 1, dense_smem, fits_dev, prog_dev, args_dev, stream));
       else
@@ -781,10 +796,14 @@ int sgdnet_session_run_epochs(sgdnet_session* s, int32_t lambda_ind, int32_t n_e
       CK(cudaMemcpyAsync(e.prog_dev, e.prog_host, sizeof(Progress), cudaMemcpyHostToDevice, e.stream));
       if (!e.stage_indices(j, ne)) return fail(SGDNET_ERR_RNG, "sampling-index source exhausted");
       CK(cudaMemcpyAsync(j.seq_dev, j.seq_pin, size_t(ne) * j.dev.n * sizeof(uint32_t), cudaMemcpyHostToDevice, e.stream));
-      e.args_host[0] = RoundArgs{j.seq_dev, ne, 1};
+      e.args_host[0] = RoundArgs{j.seq_dev, j.dep_dev, j.dup_dev, ne, 1};
       CK(cudaMemcpyAsync(e.args_dev, e.args_host, sizeof(RoundArgs), cudaMemcpyHostToDevice, e.stream));
       if (e.variant != Variant::Dense) { CK(launch_lag_scaling(1, e.fits_dev, e.prog_dev, e.stream)); ++e.launches; }
       CK(cudaEventRecord(e.ev0, e.stream));
+      if (e.variant == Variant::SparseK1) {
+        CK(launch_wave_deps(1, e.fits_dev, e.prog_dev, e.args_dev, e.max_rows_per_launch, e.sms, e.stream));
+        ++e.launches;
+      }
       if (e.variant == Variant::Dense)
         CK(launch_saga_dense(1, j.dev.K == 1, e.dense_smem, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
       else

@@ -10,6 +10,8 @@ namespace sgd {
 // Per-fit arguments that change with every round of launches.
 struct RoundArgs {
   const uint32_t* seq;   // n * n_epochs sample indices for this launch
+  uint16_t* dep;         // sparse K == 1: [n * n_epochs][32] conflict codes written by wave_deps_kernel
+  uint8_t* dup;          // sparse K == 1: [n * n_epochs] distance to the last in-window row of the same sample
   int32_t n_epochs;      // epochs this launch may run (0 => the fit sits this round out)
   int32_t flags;         // bit 0: measurement mode - run exactly n_epochs, ignore convergence, stay kRunning
 };
@@ -20,6 +22,11 @@ cudaError_t launch_saga_dense(int n_fits, bool scalar, size_t smem, FitDev* fits
                               cudaStream_t st);
 cudaError_t launch_saga_sparse(int n_fits, bool fast_k1, FitDev* fits, Progress* prog, const RoundArgs* args,
                                cudaStream_t st);
+
+// Conflict codes of the staged sequences for the wavefront kernel (sparse K == 1); must precede launch_saga_sparse.
+cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* prog, const RoundArgs* args,
+                             int64_t max_rows, int sms, cudaStream_t st);
+int wave_warps();
 
 // passes.cu
 cudaError_t launch_lag_scaling(int n_fits, FitDev* fits, Progress* prog, cudaStream_t st);
