@@ -158,6 +158,30 @@ __device__ __forceinline__ double penalty_scalar(int pen, double w, double gs, c
   return (factor < 1.0) ? v * (1.0 - factor / c.w_scale) : 0.0;
 }
 
+// sgd_exp for the solver's serial chain: the same operations and the same bits as sgd_exp (include/sgdnet_arith.h),
+// arranged so that arguments whose result is a normal number run straight through (one never-taken branch at the
+// end instead of five early exits); everything else goes to sgd_exp itself.
+__device__ __forceinline__ double sgd_exp_inrange(double x) {
+  const double kInvStep = 46.16624130844683, kStepHi = 0.021660849392446835, kStepLo = 5.145609244655338e-14;
+  const double kShift = 6755399441055744.0;
+  const double kd = fma(x, kInvStep, kShift) - kShift;
+  const int32_t k = static_cast<int32_t>(kd);
+  double r = fma(-kd, kStepHi, x);
+  r = fma(-kd, kStepLo, r);
+  double p = 1.0 / 720.0;
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  const double q = fma(r * r, p, r);
+  const int32_t j = k & 31, m = k >> 5;
+  const double thi = sgd_exp_tab_dev[2 * j], tlo = sgd_exp_tab_dev[2 * j + 1];
+  const double res = thi + fma(thi, q, tlo);
+  const double out = res * __longlong_as_double(static_cast<long long>(m + 1023) << 52);
+  if (!(x >= -707.0 && x <= 709.0)) return sgd_exp(x);   // also NaN; there m + 1023 may leave [2, 2046]
+  return out;
+}
+
 // ---- families, scalar (K == 1)
 __device__ __forceinline__ double gradient_scalar(int family, double lp, double y) {
   if (family == kBinomial) return 1.0 - y - 1.0 / (1.0 + sgd_exp(lp));
@@ -209,6 +233,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (never suspends)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)

@@ -98,7 +98,7 @@ struct FitJob {
   uint64_t generated = 0;
   uint32_t* seq_dev = nullptr;
   uint32_t* seq_pin = nullptr;
-  uint16_t* dep_dev = nullptr;        // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
+  uint64_t* dep_dev = nullptr;        // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
   uint8_t* dup_dev = nullptr;
   int epochs_per_launch = 1;
   bool done = false;
@@ -258,7 +258,7 @@ struct Engine {
     job.seq_dev = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
     job.seq_pin = arena.host<uint32_t>(size_t(epl) * d.n);
     if (d.sparse && K == 1 && !f.standardize) {
-      job.dep_dev = arena.alloc<uint16_t>(size_t(epl) * d.n * 32, false);
+      job.dep_dev = arena.alloc<uint64_t>(size_t(epl) * d.n * 32, false);
       job.dup_dev = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
     }
     jobs.push_back(std::move(job));

@@ -10,7 +10,7 @@ namespace sgd {
 // Per-fit arguments that change with every round of launches.
 struct RoundArgs {
   const uint32_t* seq;   // n * n_epochs sample indices for this launch
-  uint16_t* dep;         // sparse K == 1: [n * n_epochs][32] conflict codes written by wave_deps_kernel
+  uint64_t* dep;         // sparse K == 1: [n * n_epochs][32] conflict codes written by wave_deps_kernel
   uint8_t* dup;          // sparse K == 1: [n * n_epochs] distance to the last in-window row of the same sample
   int32_t n_epochs;      // epochs this launch may run (0 => the fit sits this round out)
   int32_t flags;         // bit 0: measurement mode - run exactly n_epochs, ignore convergence, stay kRunning

@@ -103,14 +103,15 @@ __device__ __forceinline__ bool block_converged(double mc, double ms, double* re
 //
 //  - rdy[q]    completes when row q's dot product and per-sample operands are in the chain queue.
 //  - gok[q]    completes when the chain warp has published g_change of row q (and stored the gradient memory).
-//  - fdone[q]  completes when row q's scatter is visible (what a conflicting later row waits for).
+//  - fdone[q]  completes when row q's scatter is visible in HBM (only rows behind a serial row wait for it; a
+//              conflict with an ordinary row in flight is resolved through the forwarding buffer after gok).
 //  - done[q]   like fdone but chained in row order: "done(q)" means every row <= q is complete, which bounds the rows
 //              in flight to S consecutive ones (the window wave_deps_kernel looked at).
 //  - a row whose nonzeros do not fit a ring slot, or at which the wscale reset (src/saga-sparse.h:285-295) fires,
 //    is run serially: it waits for every earlier row, and the rows after it wait for it.
 constexpr int kWSlots = 32;     // row ring depth: S rows held by the workers + rows in flight from HBM
 constexpr int kSeq = 32;        // per-row barrier / queue rings (indexed by row sequence number)
-static_assert(kChunks == 4, "conflict codes pack four 4-bit distances per lane");
+static_assert(kChunks == 4, "conflict codes pack four 16-bit entries per lane");
 
 struct WaveSlotMeta {
   uint32_t s;
@@ -124,7 +125,11 @@ struct WaveSlotMeta {
 struct __align__(128) WaveSmem {
   double val[kWSlots][kCap];
   int32_t idx[kWSlots][kCap];
-  uint16_t code[kWSlots][32];
+  uint64_t code[kWSlots][32];   // per lane: four 16-bit conflict entries (wave_deps_kernel)
+  double fw_w[kSeq][kCap];      // forwarding: a row's caught-up (w, g_sum) and its x values by nonzero position, for
+  double fw_g[kSeq][kCap];      //   the rows that touch the same feature while it is still in flight: they redo
+  double fw_x[kSeq][kCap];      //   the row's coefficient step themselves as soon as its g_change is known
+  double c_sc[kSeq], c_step1[kSeq], c_thr1[kSeq];   // the row's step constants (functions of its wscale)
   WaveSlotMeta meta[kWSlots];
   uint64_t full[kWSlots];
   uint64_t empty[kWSlots];
@@ -137,6 +142,10 @@ struct __align__(128) WaveSmem {
   double q_gm[kSeq];      //                  gradient memory of the sample
   double q_gch[kSeq];     // chain -> worker: g_change
   uint32_t q_s[kSeq];     // worker -> chain: sample id
+#ifdef SGD_WAVE_PROF
+  uint32_t q_dmin[kSeq];
+  long long ts_gok[kSeq], ts_fdone[kSeq], ts_wake[kSeq], ts_rdy[kSeq], ts_gokwake[kSeq], ts_a[kSeq], ts_b[kSeq], ts_c[kSeq];
+#endif
   double red[2 * 32];
   double wscale_s;
 };
@@ -154,8 +163,17 @@ __device__ __forceinline__ void st_state(FeatState* p, double w, double g, uint3
                : "memory");
 }
 
-__device__ __forceinline__ void wait_row(uint64_t* ring, int64_t q) {
-  mbar_wait(&ring[q % kSeq], static_cast<uint32_t>((q / kSeq) & 1));
+#ifndef SGD_SLEEP_NS
+#define SGD_SLEEP_NS 100
+#endif
+__device__ __forceinline__ void wait_row(uint64_t* ring, uint32_t q) {
+  mbar_wait(&ring[q % kSeq], (q / kSeq) & 1u);
+}
+// for waits that are long by design (a worker ahead of the chain): leave the issue slots to the other warps
+__device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
+  uint64_t* bar = &ring[q % kSeq];
+  const uint32_t par = (q / kSeq) & 1u;
+  while (!mbar_test_wait(bar, par)) __nanosleep(SGD_SLEEP_NS);
 }
 
 // gch / n with n an integer below 2^32: q = a*(1/n) corrected once with the exact residual is the correctly rounded
@@ -173,9 +191,12 @@ __device__ __forceinline__ double div_by_n(double a, double nd, double rn) {
 }
 
 // ---- conflict codes: for every row instance q = epoch*n + t of the staged sequence and every nonzero position e of
-// its row, the distance d in 1..window to the most recent earlier row OF THE SAME EPOCH that holds the same feature
-// (0 = none within the window). A row too long for a ring slot conflicts with everything. Lane l of the solver reads
-// one 16-bit word holding the codes of positions l, l+32, l+64, l+96.
+// its row, a 16-bit entry about the most recent earlier row OF THE SAME EPOCH within `window` rows that holds the same
+// feature: bits 0-3 its distance d (0 = no such row), bits 4-10 the feature's position in that row (where its
+// forwarded state sits in shared memory), bit 11 "read it from HBM instead" (that row was too long for a ring slot and
+// ran serially). Lane l of a worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
+constexpr uint32_t kCodeGlobal = 1u << 11;
+
 __global__ void __launch_bounds__(256)
 wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
                  int window) {
@@ -195,12 +216,14 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
     const uint32_t s = eseq[t];
     const RowInfo ri = f.rows[s];
     int j[kChunks];
+    uint32_t ent[kChunks];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int e = c * 32 + lane;
       j[c] = (ri.nnz <= kCap && e < ri.nnz) ? ci[ri.start + e] : -1;
+      ent[c] = 0;
     }
-    uint32_t code = 0, dupd = 0;
+    uint32_t dupd = 0;
     const int dmax = static_cast<int>(t < window ? t : window);
     for (int d = 1; d <= dmax; ++d) {
       const uint32_t s2 = eseq[t - d];
@@ -210,24 +233,519 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
       const int32_t* __restrict__ c2 = ci + r2.start;
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        if (j[c] < 0 || ((code >> (4 * c)) & 15u) != 0) continue;
-        bool hit = r2.nnz > kCap;
-        if (!hit) {
-          int lo = 0, hi = r2.nnz;           // first position with c2[pos] >= j[c]
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
-          }
-          hit = lo < r2.nnz && c2[lo] == j[c];
+        if (j[c] < 0 || ent[c] != 0) continue;
+        if (r2.nnz > kCap) {
+          ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
+          continue;
         }
-        if (hit) code |= static_cast<uint32_t>(d) << (4 * c);
+        int lo = 0, hi = r2.nnz;             // first position with c2[pos] >= j[c]
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
+        }
+        if (lo < r2.nnz && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
       }
     }
-    ra.dep[q * 32 + lane] = static_cast<uint16_t>(code);
+    ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
     if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd);
   }
 }
 
+#ifdef SGD_WAVE_PROF
+__device__ long long g_wave_prof[20][8];
+__device__ long long g_wave_stall[16][2];
+__device__ long long g_wave_path[12];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, a, b) prof_acc[slot] += (b) - (a)
+#define PROF_ARG , long long* prof_acc
+#define PROF_PASS , prof_acc
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, a, b)
+#define PROF_ARG
+#define PROF_PASS
+#endif
+
+// A taken branch costs a lone warp about 23 cycles on sm_100a (scripts/microbench.cu: a dependent DFMA is 8), and the
+// solver is a handful of lone warps, so the hot paths below are written to compile to straight-line predicated code:
+// loads use clamped indices instead of guards, stores carry their predicate into the instruction, "skip when the lag
+// is zero" is a select. None of this changes a single floating point operation that reaches the state.
+template <int PEN>
+__device__ __forceinline__ double penalty_k1(double w, double gs, double step, double thr) {
+  const double v = w - step * gs;
+  return (PEN == kElasticNet) ? soft_threshold(v, thr) : v;   // K == 1 never uses the group penalty
+}
+
+__device__ __forceinline__ void st_state_if(bool pred, FeatState* p, double w, double g, uint32_t lag) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pp;\n"
+      "setp.ne.b32 pp, %5, 0;\n"
+      "@pp st.global.v4.b64 [%0], {%1,%2,%3,%4};\n"
+      "}\n" ::"l"(p),
+      "l"(__double_as_longlong(w)), "l"(__double_as_longlong(g)), "l"(static_cast<unsigned long long>(lag)), "l"(0ull),
+      "r"(static_cast<int>(pred))
+      : "memory");
+}
+
+struct WaveConst {
+  uint32_t n;
+  int p, family;
+  bool fit_intercept;
+  double nd, gamma, r, sc2, bg;
+  const double* ls_table;
+  FeatState* st;
+};
+
+// ------------------------------------------------------------------ producer: lane l feeds ring slot l
+// Warp-synchronous: the lanes load the sample index, row descriptor, response and duplicate code of their next row
+// together (32 independent requests in flight), one batch ahead of the batch being issued, then the warp polls the
+// slots' "empty" barriers and issues each row's bulk copies as soon as its slot is released.
+__device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const RoundArgs& ra, int ep, uint32_t q_base,
+                                           uint32_t n, int lane) {
+  const uint32_t* __restrict__ eseq = ra.seq + size_t(ep) * n;
+  const uint8_t* __restrict__ edup = ra.dup + size_t(ep) * n;
+  const uint64_t* __restrict__ edep = ra.dep + size_t(ep) * n * 32;
+  uint32_t t = (static_cast<uint32_t>(lane) - q_base) % kWSlots;   // q = q_base + t lands on slot `lane`
+  bool have = t < n;
+  uint32_t s = 0, dv = 0;
+  RowInfo ri{};
+  double y = 0.0;
+  if (have) {
+    s = eseq[t];
+    dv = edup[t];
+    ri = f.rows[s];
+    y = f.yt[s];
+  }
+  while (__any_sync(0xffffffffu, have)) {
+    const uint32_t tn = t + kWSlots;
+    const bool have_n = have && tn < n;
+    uint32_t sn = 0, dvn = 0;
+    RowInfo rin{};
+    double yn = 0.0;
+    if (have_n) {
+      sn = eseq[tn];
+      dvn = edup[tn];
+      rin = f.rows[sn];
+      yn = f.yt[sn];
+    }
+    bool pending = have;
+    const uint32_t q = q_base + t;
+    const uint32_t par = ((q / kWSlots) & 1u) ^ 1u;
+    while (__any_sync(0xffffffffu, pending)) {
+      if (pending && mbar_try_wait(&sm.empty[lane], par)) {
+        WaveSlotMeta m;
+        m.s = s;
+        m.nnz = ri.nnz;
+        m.start = ri.start;
+        m.y = y;
+        m.dup = dv;
+        m.pad_ = 0;
+        sm.meta[lane] = m;
+        if (ri.nnz > 0 && ri.nnz <= kCap) {
+          const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
+          const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
+          mbar_expect_tx(&sm.full[lane], bi + bv + 256u);
+          bulk_g2s(sm.idx[lane], f.ci + ri.start, bi, &sm.full[lane]);
+          bulk_g2s(sm.val[lane], f.cv + ri.start, bv, &sm.full[lane]);
+          bulk_g2s(sm.code[lane], edep + size_t(t) * 32, 256u, &sm.full[lane]);
+        } else {
+          mbar_arrive(&sm.full[lane]);
+        }
+        pending = false;
+      }
+      if (__any_sync(0xffffffffu, pending)) __nanosleep(200);   // the ring is 32 rows deep: no hurry
+    }
+    t = tn;
+    have = have_n;
+    s = sn;
+    dv = dvn;
+    ri = rin;
+    y = yn;
+  }
+}
+
+// ------------------------------------------------------------------ chain warp: the serial scalar recurrence
+// lp = dot + b; Gradient (src/families.h:89-96, 161-168); g_change; intercept step (src/saga-sparse.h:300-304).
+template <int FAMILY, bool INTERCEPT>
+__device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const WaveConst& k, uint32_t q_base, int lane,
+                                        double& b_io, double& gsi_io PROF_ARG) {
+  const uint32_t n = k.n;
+  const double nd = k.nd, rn = 1.0 / k.nd, gamma = k.gamma;
+  double b_reg = b_io, gsi_reg = gsi_io;
+  double* __restrict__ gmem = f.gmem;
+  PROF_T(c00);
+  wait_row(sm.rdy, q_base);
+  PROF_T(c01);
+  PROF_ADD(0, c00, c01);
+  double dot = sm.q_dot[q_base % kSeq], ya = sm.q_ya[q_base % kSeq], gm = sm.q_gm[q_base % kSeq];
+  uint32_t s = sm.q_s[q_base % kSeq];
+#pragma unroll 2
+  for (uint32_t t = 0; t < n; ++t) {
+    const uint32_t q = q_base + t;
+    const int sq = static_cast<int>(q % kSeq), sq1 = static_cast<int>((q + 1u) % kSeq);
+    PROF_T(c1);
+    // probe the next row's operands while this row's arithmetic runs (non-blocking; the ring has a spare barrier
+    // phase, so probing one row past the epoch's end is harmless)
+    const bool next_ready = mbar_test_wait(&sm.rdy[sq1], ((q + 1u) / kSeq) & 1u);
+    const double lp = dot + b_reg;
+    double g;
+    if (FAMILY == kBinomial) g = ya - 1.0 / (1.0 + sgd_exp_inrange(lp));   // ya = 1 - y
+    else g = lp - ya;
+    const double gch = g - gm;
+    if (lane == 0) {
+      sm.q_gch[sq] = gch;
+      gmem[s] = g;
+#ifdef SGD_WAVE_PROF
+      sm.ts_gok[sq] = clock64();
+#endif
+      mbar_arrive(&sm.gok[sq]);
+    }
+    if (INTERCEPT) {
+      const double gn = div_by_n(gch, nd, rn);
+      gsi_reg += gn;
+      b_reg -= gamma * (gsi_reg * 0.01 + gn);
+    }
+#ifdef SGD_WAVE_PROF
+    const long long c2 = (b_reg != 12345.678) ? clock64() : 0;
+    PROF_ADD(1, c1, c2);
+#endif
+    if (t + 1u < n) {
+      if (!next_ready) mbar_wait(&sm.rdy[sq1], ((q + 1u) / kSeq) & 1u);
+      dot = sm.q_dot[sq1];
+      ya = sm.q_ya[sq1];
+      gm = sm.q_gm[sq1];
+      s = sm.q_s[sq1];
+    }
+#ifdef SGD_WAVE_PROF
+    const long long c3 = (dot != 12345.678) ? clock64() : 0;
+    PROF_ADD(0, c2, c3);
+    if (t + 1u < n && lane == 0) {
+      const uint32_t dm = sm.q_dmin[sq1];
+      g_wave_stall[dm][0] += 1;
+      g_wave_stall[dm][1] += c3 - c2;
+      if (dm == 1) {   // path of a distance-1 conflict: gok(q) -> gok wake -> fdone(q) -> late wake(q+1) -> rdy(q+1) -> here
+        g_wave_path[0] += 1;
+        g_wave_path[1] += sm.ts_gokwake[sq] - sm.ts_gok[sq];
+        g_wave_path[2] += sm.ts_fdone[sq] - sm.ts_gokwake[sq];
+        g_wave_path[3] += sm.ts_wake[sq1] - sm.ts_fdone[sq];
+        g_wave_path[4] += sm.ts_rdy[sq1] - sm.ts_wake[sq1];
+        g_wave_path[5] += c3 - sm.ts_rdy[sq1];
+        g_wave_path[6] += c3 - sm.ts_gok[sq];
+        g_wave_path[7] += sm.ts_a[sq1] - sm.ts_wake[sq1];
+        g_wave_path[8] += sm.ts_b[sq1] - sm.ts_a[sq1];
+        g_wave_path[9] += sm.ts_rdy[sq1] - sm.ts_b[sq1];
+      }
+    }
+#endif
+  }
+  b_io = b_reg;
+  gsi_io = gsi_reg;
+}
+
+// ------------------------------------------------------------------ worker warp: rows t = warp, warp+S, ...
+// PEN = kRidge | kElasticNet; IDENT: alpha*gamma == 0 (lasso or lambda == 0), so wscale stays exactly 1,
+// lag_scaling[m] is exactly m, and every "/ wscale" is a division by 1.0 (exact, skipped).
+template <int S, int PEN, bool IDENT>
+__device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const WaveConst& k, uint32_t q_base, int warp,
+                                         int lane PROF_ARG) {
+  const uint32_t n = k.n;
+  const double gamma = k.gamma, r = k.r, sc2 = k.sc2, bg = k.bg;
+  const double* __restrict__ ls_table = k.ls_table;
+  FeatState* __restrict__ st = k.st;
+  const int p = k.p;
+
+  double ws = 1.0;        // wscale at the start of step t_sim (before that step's reset test)
+  uint32_t t_sim = 0;
+  for (uint32_t t = warp; t < n; t += S) {
+    const uint32_t q = q_base + t;
+    const int slot = static_cast<int>(q % kWSlots);
+    const int sq = static_cast<int>(q % kSeq);
+
+    // deterministic wscale track: steps t_sim .. t-1 belong to other workers (all within the window)
+    uint32_t force = 0;   // distance to the most recent reset row among them (0 = none)
+    bool reset_here = false;
+    double ws_next = 1.0, step0 = gamma, sc = -gamma, step1 = gamma, thr1 = bg;   // IDENT: x / 1.0 == x exactly
+    if (!IDENT) {
+      while (t_sim < t) {
+        if (ws < kSmall) {
+          ws = 1.0;
+          force = t - t_sim;
+        }
+        ws *= r;
+        ++t_sim;
+      }
+      reset_here = ws < kSmall;
+      ws_next = (reset_here ? 1.0 : ws) * r;   // wscale after this step
+      step0 = gamma / ws;
+      sc = -gamma / ws_next;
+      step1 = gamma / ws_next * 1.0;
+      thr1 = bg / ws_next;
+    }
+
+    PROF_T(w0);
+    mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
+    PROF_T(w1);
+    PROF_ADD(0, w0, w1);
+    const WaveSlotMeta m = sm.meta[slot];
+    const bool serial = reset_here || m.nnz > kCap;
+    const double ya = (k.family == kBinomial) ? 1.0 - m.y : m.y;
+
+    if (!serial) {
+      // ---- the row and its conflict codes into registers, then give the slot back
+      int jr[kChunks];
+      bool valid[kChunks];
+      double vr[kChunks], wr[kChunks], gr[kChunks];
+      uint32_t lr[kChunks], dr[kChunks];   // dr: conflict entry (distance | position << 4 | kCodeGlobal)
+      const uint64_t code = sm.code[slot][lane];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int e = c * 32 + lane;
+        valid[c] = e < m.nnz;
+        jr[c] = valid[c] ? sm.idx[slot][e] : 0;          // clamped: invalid positions gather feature 0 and drop it
+        vr[c] = valid[c] ? sm.val[slot][e] : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[slot]);
+      // ---- gather every position now; the few that a row in flight touches are re-read below
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) ld_state(st + jr[c], wr[c], gr[c], lr[c]);
+      const double gm_early = f.gmem[m.s];
+      // distance to the nearest row in flight that touches the feature; a reset row in the window touches all
+      bool late = false;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t d = static_cast<uint32_t>(code >> (16 * c)) & 0xffffu;
+        if (!IDENT && force != 0 && (d == 0 || (d & 15u) >= force)) d = force | kCodeGlobal;
+        d = valid[c] ? d : 0u;
+        dr[c] = d;
+        late = late || d != 0;
+      }
+      PROF_T(w2);
+      PROF_ADD(1, w1, w2);
+      // LaggedUpdate(k = t) on one gathered feature (src/saga-sparse.h:76-100, src/penalties.h); the result is only
+      // taken when the lag is non-zero, exactly like the reference's `if (lagged_amount != 0)`
+      auto caught_up = [&](double w, double g, uint32_t lg) {
+        const uint32_t lagged = t - lg;
+        const double scal = IDENT ? static_cast<double>(lagged) : ls_table[lagged < n ? lagged : 0u];
+        const double bgs = bg * scal;
+        const double w_new = penalty_k1<PEN>(w, g, step0 * scal, IDENT ? bgs : bgs / ws);
+        return (lagged != 0) ? w_new : w;
+      };
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) wr[c] = caught_up(wr[c], gr[c], lr[c]);
+      double gm = gm_early;
+      // ---- rows in flight. A feature that row t-d (d < S) also holds is not read from HBM: as soon as the chain
+      // warp has published that row's g_change, this warp repeats the row's own coefficient step on the state it
+      // forwarded (same operands, same operations, so the same bits it scatters) and catches the result up.
+      // Kept warp-uniform (a warp that diverges around a wait pays hundreds of cycles per later shuffle): the warp
+      // waits for every row any lane needs, then each lane swaps the state in by select.
+      uint32_t need_g = 0, need_f = 0;   // bit d: g_change of / HBM scatter of row t-d is needed
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const uint32_t bit = (dr[c] != 0) ? (1u << (dr[c] & 15u)) : 0u;
+        need_g |= (dr[c] & kCodeGlobal) ? 0u : bit;
+        need_f |= (dr[c] & kCodeGlobal) ? bit : 0u;
+      }
+      need_g = __reduce_or_sync(0xffffffffu, need_g) | ((m.dup != 0) ? (1u << m.dup) : 0u);
+      need_f = __reduce_or_sync(0xffffffffu, need_f);
+      if ((need_g | need_f) != 0) {
+        // oldest first: those are complete already, the nearest row is the one worth sleeping on
+        for (uint32_t rest = need_f; rest != 0;) {
+          const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
+          rest &= ~(1u << d);
+          wait_row(sm.fdone, q - d);
+        }
+        for (uint32_t rest = need_g; rest != 0;) {
+          const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
+          rest &= ~(1u << d);
+          wait_row(sm.gok, q - d);
+        }
+        if (m.dup != 0) gm = f.gmem[m.s];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const uint32_t d = dr[c] & 15u, sqd = (q - d) % kSeq, pos = (dr[c] >> 4) & 127u;
+          const bool fwd = dr[c] != 0 && (dr[c] & kCodeGlobal) == 0;
+          const double gx = sm.fw_x[sqd][pos] * sm.q_gch[sqd];
+          const double fg = sm.fw_g[sqd][pos];
+          const double w_new = penalty_k1<PEN>(sm.fw_w[sqd][pos] + gx * (IDENT ? sc : sm.c_sc[sqd]), fg,
+                                               IDENT ? step1 : sm.c_step1[sqd], IDENT ? thr1 : sm.c_thr1[sqd]);
+          const double g_new = fg + gx * sc2;
+          wr[c] = fwd ? caught_up(w_new, g_new, t - d + 1u) : wr[c];   // row t-d left lag = t-d+1
+          gr[c] = fwd ? g_new : gr[c];
+        }
+        if (need_f != 0) {                          // behind a serial row (rare): re-read HBM
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            if (dr[c] & kCodeGlobal) {
+              ld_state(st + jr[c], wr[c], gr[c], lr[c]);
+              wr[c] = caught_up(wr[c], gr[c], lr[c]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // ---- forward this row's caught-up state (read by the rows that conflict with it, after its gok)
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        sm.fw_w[sq][c * 32 + lane] = wr[c];
+        sm.fw_g[sq][c * 32 + lane] = gr[c];
+        sm.fw_x[sq][c * 32 + lane] = vr[c];
+      }
+      if (!IDENT && lane == 0) {
+        sm.c_sc[sq] = sc;
+        sm.c_step1[sq] = step1;
+        sm.c_thr1[sq] = thr1;
+      }
+      PROF_T(w3);
+      PROF_ADD(2, w2, w3);
+#ifdef SGD_WAVE_PROF
+      {
+        long long tw = clock64();
+        for (int o = 16; o > 0; o >>= 1) tw = max(tw, __shfl_xor_sync(0xffffffffu, tw, o));
+        if (lane == 0) sm.ts_wake[sq] = tw;
+      }
+#endif
+      // ---- the sparse dot product: position e -> running sum e mod 32, then the butterfly (sgdnet_arith.h)
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const double a2 = acc + vr[c] * wr[c];
+        acc = valid[c] ? a2 : acc;
+      }
+#ifdef SGD_WAVE_PROF
+      if (lane == 0) sm.ts_a[sq] = (acc != 12345.678) ? clock64() : 0;
+#endif
+      double dot = warp_sum(acc);
+      if (!IDENT) dot = dot * ws;
+#ifdef SGD_WAVE_PROF
+      if (lane == 0) sm.ts_b[sq] = (dot != 12345.678) ? clock64() : 0;
+      uint32_t dmin = 16;
+      for (int c = 0; c < kChunks; ++c) if (dr[c] != 0) dmin = min(dmin, dr[c] & 15u);
+      for (int o = 16; o > 0; o >>= 1) dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+      if (lane == 0) sm.q_dmin[sq] = dmin & 15u;
+#endif
+      __syncwarp();                                 // the forwarded state of every lane precedes the arrive
+      if (lane == 0) {
+        sm.q_dot[sq] = dot;
+        sm.q_ya[sq] = ya;
+        sm.q_gm[sq] = gm;
+        sm.q_s[sq] = m.s;
+#ifdef SGD_WAVE_PROF
+        sm.ts_rdy[sq] = clock64();
+#endif
+        mbar_arrive(&sm.rdy[sq]);
+      }
+      PROF_T(w4);
+      PROF_ADD(3, w3, w4);
+      wait_row(sm.gok, q);
+      const double gch = sm.q_gch[sq];
+      PROF_T(w5);
+      PROF_ADD(4, w4, w5);
+#ifdef SGD_WAVE_PROF
+      if (lane == 0) sm.ts_gokwake[sq] = w5;
+#endif
+      // ---- AddWeighted(w), LaggedUpdate(k = t+1, lag 1), AddWeighted(g_sum), scatter
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const double gx = vr[c] * gch;
+        const double w = penalty_k1<PEN>(wr[c] + gx * sc, gr[c], step1, thr1);
+        st_state_if(valid[c], st + jr[c], w, gr[c] + gx * sc2, t + 1u);
+      }
+    } else {
+      // ---- serial row: every earlier row is complete before anything is read; operands are used in place
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[slot]);
+      if (t > 0) wait_row(sm.done, q - 1u);
+      const double gm = f.gmem[m.s];
+      const int32_t* __restrict__ ci = f.ci + m.start;
+      const double* __restrict__ cv = f.cv + m.start;
+      double acc = 0.0;
+      for (int e = lane; e < m.nnz; e += 32) {
+        const int j = ci[e];
+        double w, gs;
+        uint32_t lg;
+        ld_state(st + j, w, gs, lg);
+        const uint32_t lagged = t - lg;
+        if (lagged != 0) {
+          const double scal = IDENT ? static_cast<double>(lagged) : ls_table[lagged];
+          const double bgs = bg * scal;
+          w = penalty_k1<PEN>(w, gs, step0 * scal, IDENT ? bgs : bgs / ws);
+          st_state(st + j, w, gs, t);
+        }
+        acc += cv[e] * w;
+      }
+      double dot = warp_sum(acc);
+      if (!IDENT) dot = dot * ws;
+      if (lane == 0) {
+#ifdef SGD_WAVE_PROF
+        sm.q_dmin[sq] = 15;
+#endif
+        sm.q_dot[sq] = dot;
+        sm.q_ya[sq] = ya;
+        sm.q_gm[sq] = gm;
+        sm.q_s[sq] = m.s;
+        mbar_arrive(&sm.rdy[sq]);
+      }
+      if (reset_here) {
+        // Reset(t) over all features, lag = t (src/saga-sparse.h:285-295)
+        __syncwarp();
+        for (int j = lane; j < p; j += 32) {
+          double w, gs;
+          uint32_t lg;
+          ld_state(st + j, w, gs, lg);
+          const uint32_t lagged = t - lg;
+          if (lagged != 0) {
+            const double scal = ls_table[lagged];
+            const double bgs = bg * scal;
+            w = penalty_k1<PEN>(w, gs, step0 * scal, bgs / ws);
+          }
+          st_state(st + j, w * ws, gs, t);
+        }
+        __syncwarp();
+      }
+      wait_row(sm.gok, q);
+      const double gch = sm.q_gch[sq];
+      for (int e = lane; e < m.nnz; e += 32) {
+        const int j = ci[e];
+        const double gx = cv[e] * gch;
+        double w, gs;
+        uint32_t lg;
+        ld_state(st + j, w, gs, lg);
+        w = penalty_k1<PEN>(w + gx * sc, gs, step1, thr1);
+        st_state(st + j, w, gs + gx * sc2, t + 1u);
+      }
+    }
+    // ---- completion chained in row order: the row's HBM scatter is visible and so is every earlier row's
+    __syncwarp();
+    PROF_T(w6);
+    if (lane == 0) {
+#ifdef SGD_WAVE_PROF
+      sm.ts_fdone[sq] = clock64();
+#endif
+      mbar_arrive(&sm.fdone[sq]);
+      if (t > 0) wait_row(sm.done, q - 1u);
+      mbar_arrive(&sm.done[sq]);
+    }
+    PROF_T(w7);
+    PROF_ADD(5, w1, w6);
+    PROF_ADD(6, w6, w7);
+    ws = ws_next;
+    t_sim = t + 1u;
+  }
+  // wscale after the epoch's last step (identical in every worker)
+  if (!IDENT) {
+    while (t_sim < n) {
+      if (ws < kSmall) ws = 1.0;
+      ws *= r;
+      ++t_sim;
+    }
+  }
+  if (warp == 0 && lane == 0) sm.wscale_s = IDENT ? 1.0 : ws;
+}
+
+// One CTA per fit. The fits of a batch may differ in family, penalty and in whether wscale moves (cv alpha grids), so
+// the specialisations are chosen per CTA (and per role) at run time.
 template <int S>
 __global__ void __launch_bounds__((S + 2) * 32, 1)
 saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const RoundArgs* __restrict__ args) {
@@ -243,19 +761,24 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
   const FitDev& f = fits[fit_id];
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int p = f.p;
-  const int64_t n = f.n;
-  const uint32_t n32 = static_cast<uint32_t>(n);
-  const double nd = static_cast<double>(n32);
-  const int family = f.family, pen = f.penalty;
-  const bool fit_intercept = f.fit_intercept != 0;
-
   const int li = pg.lambda_ind;
-  const double gamma = f.gamma[li], alpha = f.alpha[li], beta = f.beta[li];
-  const double r = 1.0 - alpha * gamma;
-  const bool identity = (r == 1.0);          // lasso: wscale == 1 and lag_scaling[m] == m exactly
-  const double sc2 = 1.0 / nd;
-  const double bg = beta * gamma;            // (beta*gamma)*1.0
+  WaveConst k;
+  k.n = static_cast<uint32_t>(f.n);
+  k.p = f.p;
+  k.family = f.family;
+  k.fit_intercept = f.fit_intercept != 0;
+  k.nd = static_cast<double>(k.n);
+  k.gamma = f.gamma[li];
+  const double alpha = f.alpha[li], beta = f.beta[li];
+  k.r = 1.0 - alpha * k.gamma;               // wscale_update
+  k.sc2 = 1.0 / k.nd;
+  k.bg = beta * k.gamma;                     // (beta*gamma)*1.0
+  k.ls_table = f.lag_scaling;
+  k.st = f.st;
+  const bool ident = (k.r == 1.0);
+  const int pen = f.penalty;
+  const uint32_t n = k.n;
+  const int p = k.p;
 
   if (tid == 0) {
     for (int i = 0; i < kWSlots; ++i) {
@@ -272,318 +795,54 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
   }
   __syncthreads();
 
-  FeatState* __restrict__ st = f.st;
   double b_reg = f.b[0], gsi_reg = f.gsi[0];   // live in the chain warp
+#ifdef SGD_WAVE_PROF
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
   uint32_t it_outer = pg.it_outer, epochs_done = 0;
   bool finished = false;
-  int64_t q_base = 0;       // sequence number of the first row of the current epoch
+  uint32_t q_base = 0;      // sequence number (mod 2^32) of the first row of the current epoch
 
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep, q_base += n) {
-    const uint32_t* __restrict__ eseq = ra.seq + size_t(ep) * n;
-
     if (warp == kProducer) {
-      // ------------------------------------------------------------------ producer: lane l feeds ring slot l
-      // Warp-synchronous: the lanes load the sample index, row descriptor, response and duplicate code of their next
-      // row together (32 independent requests in flight), one batch ahead of the batch being issued, then the warp
-      // polls the slots' "empty" barriers and issues each row's bulk copies as soon as its slot is released.
-      const uint8_t* __restrict__ edup = ra.dup + size_t(ep) * n;
-      const uint16_t* __restrict__ edep = ra.dep + size_t(ep) * n * 32;
-      int64_t t = (lane - static_cast<int>(q_base % kWSlots) + kWSlots) % kWSlots;   // q = q_base + t lands on slot `lane`
-      bool have = t < n;
-      uint32_t s = 0, dv = 0;
-      RowInfo ri{};
-      double y = 0.0;
-      if (have) {
-        s = eseq[t];
-        dv = edup[t];
-        ri = f.rows[s];
-        y = f.yt[s];
-      }
-      while (__any_sync(0xffffffffu, have)) {
-        const int64_t tn = t + kWSlots;
-        const bool have_n = tn < n;
-        uint32_t sn = 0, dvn = 0;
-        RowInfo rin{};
-        double yn = 0.0;
-        if (have_n) {
-          sn = eseq[tn];
-          dvn = edup[tn];
-          rin = f.rows[sn];
-          yn = f.yt[sn];
-        }
-        bool pending = have;
-        const int64_t q = q_base + t;
-        const uint32_t par = static_cast<uint32_t>(((q / kWSlots) & 1) ^ 1);
-        while (__any_sync(0xffffffffu, pending)) {
-          if (pending && mbar_try_wait(&sm.empty[lane], par)) {
-            WaveSlotMeta m;
-            m.s = s;
-            m.nnz = ri.nnz;
-            m.start = ri.start;
-            m.y = y;
-            m.dup = dv;
-            m.pad_ = 0;
-            sm.meta[lane] = m;
-            if (ri.nnz > 0 && ri.nnz <= kCap) {
-              const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
-              const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
-              mbar_expect_tx(&sm.full[lane], bi + bv + 64u);
-              bulk_g2s(sm.idx[lane], f.ci + ri.start, bi, &sm.full[lane]);
-              bulk_g2s(sm.val[lane], f.cv + ri.start, bv, &sm.full[lane]);
-              bulk_g2s(sm.code[lane], edep + size_t(t) * 32, 64u, &sm.full[lane]);
-            } else {
-              mbar_arrive(&sm.full[lane]);
-            }
-            pending = false;
-          }
-        }
-        t = tn;
-        have = have_n;
-        s = sn;
-        dv = dvn;
-        ri = rin;
-        y = yn;
-      }
+      wave_producer(sm, f, ra, ep, q_base, n, lane);
     } else if (warp == kChain) {
-      // ------------------------------------------------------------------ chain warp: the serial scalar recurrence
-      const double rn = 1.0 / nd;
-      for (int64_t t = 0; t < n; ++t) {
-        const int64_t q = q_base + t;
-        const int sq = static_cast<int>(q % kSeq);
-        wait_row(sm.rdy, q);
-        const double dot = sm.q_dot[sq];
-        const double ya = sm.q_ya[sq];
-        const double gm = sm.q_gm[sq];
-        const uint32_t s = sm.q_s[sq];
-        const double lp = dot + b_reg;
-        // Gradient (src/families.h:89-96, 161-168); ya = 1 - y for the binomial family
-        const double g = (family == kBinomial) ? ya - 1.0 / (1.0 + sgd_exp(lp)) : lp - ya;
-        const double gch = g - gm;
-        if (lane == 0) {
-          sm.q_gch[sq] = gch;
-          f.gmem[s] = g;
-          mbar_arrive(&sm.gok[sq]);
-        }
-        if (fit_intercept) {
-          const double gn = div_by_n(gch, nd, rn);
-          gsi_reg += gn;
-          b_reg -= gamma * (gsi_reg * 0.01 + gn);
-        }
+      if (k.family == kBinomial) {
+        if (k.fit_intercept) wave_chain<kBinomial, true>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
+        else wave_chain<kBinomial, false>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
+      } else {
+        if (k.fit_intercept) wave_chain<kGaussian, true>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
+        else wave_chain<kGaussian, false>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
       }
     } else {
-      // ------------------------------------------------------------------ worker warp: rows t = warp, warp+S, ...
-      double ws = 1.0;        // wscale at the start of step t_sim (before that step's reset test)
-      int64_t t_sim = 0;
-      for (int64_t t = warp; t < n; t += S) {
-        const int64_t q = q_base + t;
-        const int slot = static_cast<int>(q % kWSlots);
-        const int sq = static_cast<int>(q % kSeq);
-        const uint32_t t32 = static_cast<uint32_t>(t);
-
-        // deterministic wscale track: steps t_sim .. t-1 belong to other workers (all within the window)
-        int force = 0;        // distance to the most recent reset row among them (0 = none)
-        if (!identity) {
-          while (t_sim < t) {
-            if (ws < kSmall) {
-              ws = 1.0;
-              force = static_cast<int>(t - t_sim);
-            }
-            ws *= r;
-            ++t_sim;
-          }
-        }
-        const bool reset_here = !identity && ws < kSmall;
-
-        mbar_wait(&sm.full[slot], static_cast<uint32_t>((q / kWSlots) & 1));
-        const WaveSlotMeta m = sm.meta[slot];
-        const bool serial = reset_here || m.nnz > kCap;
-        const double ya = (family == kBinomial) ? 1.0 - m.y : m.y;
-        double ws_next;       // wscale after this step
-
-        if (!serial) {
-          // ---- the row and its conflict codes into registers, then give the slot back
-          int jr[kChunks];
-          double vr[kChunks], wr[kChunks], gr[kChunks];
-          uint32_t lr[kChunks];
-          uint32_t code = (m.nnz > 0) ? sm.code[slot][lane] : 0u;
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            const int e = c * 32 + lane;
-            jr[c] = (e < m.nnz) ? sm.idx[slot][e] : -1;
-            vr[c] = (e < m.nnz) ? sm.val[slot][e] : 0.0;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.empty[slot]);
-          // a reset row in the window is a conflict on every feature
-          bool any_late = false;
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            uint32_t d = (code >> (4 * c)) & 15u;
-            if (force != 0 && (d == 0 || d > static_cast<uint32_t>(force))) d = static_cast<uint32_t>(force);
-            if (jr[c] < 0) d = 0;
-            code = (code & ~(15u << (4 * c))) | (d << (4 * c));
-            any_late = any_late || d != 0;
-          }
-          // ---- early gathers: features no row in flight touches
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c)
-            if (jr[c] >= 0 && ((code >> (4 * c)) & 15u) == 0) ld_state(st + jr[c], wr[c], gr[c], lr[c]);
-          if (m.dup != 0) wait_row(sm.fdone, q - m.dup);
-          const double gm = f.gmem[m.s];
-          // ---- late gathers: each waits for the nearest row that touches its feature
-          if (any_late) {
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-              const uint32_t d = (code >> (4 * c)) & 15u;
-              if (d != 0) {
-                wait_row(sm.fdone, q - d);
-                ld_state(st + jr[c], wr[c], gr[c], lr[c]);
-              }
-            }
-          }
-          // ---- LaggedUpdate(k = t) and the sparse dot product
-          const double step0 = gamma / ws;
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            if (jr[c] >= 0) {
-              const uint32_t lagged = t32 - lr[c];
-              if (lagged != 0) {
-                const double scal = lag_scale(identity, f.lag_scaling, lagged);
-                PenCoef pc;
-                pc.step = step0 * scal;
-                pc.bgs = bg * scal;
-                pc.thr = pc.bgs / ws;
-                pc.w_scale = ws;
-                wr[c] = penalty_scalar(pen, wr[c], gr[c], pc);
-              }
-              acc += vr[c] * wr[c];
-            }
-          }
-          const double dot = warp_sum(acc) * ws;
-          if (lane == 0) {
-            sm.q_dot[sq] = dot;
-            sm.q_ya[sq] = ya;
-            sm.q_gm[sq] = gm;
-            sm.q_s[sq] = m.s;
-            mbar_arrive(&sm.rdy[sq]);
-          }
-          // everything of the coefficient step that does not depend on the gradient
-          ws_next = ws * r;
-          const double sc = -gamma / ws_next;
-          PenCoef pc1;
-          pc1.step = gamma / ws_next * 1.0;
-          pc1.bgs = bg;
-          pc1.thr = bg / ws_next;
-          pc1.w_scale = ws_next;
-          wait_row(sm.gok, q);
-          const double gch = sm.q_gch[sq];
-          // ---- AddWeighted(w), LaggedUpdate(k = t+1, lag 1), AddWeighted(g_sum), scatter
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            if (jr[c] >= 0) {
-              const double gx = vr[c] * gch;
-              double w = wr[c] + gx * sc;
-              w = penalty_scalar(pen, w, gr[c], pc1);
-              st_state(st + jr[c], w, gr[c] + gx * sc2, t32 + 1u);
-            }
-          }
-        } else {
-          // ---- serial row: every earlier row is complete before anything is read; operands are used in place
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.empty[slot]);
-          if (q > 0) wait_row(sm.done, q - 1);
-          const double gm = f.gmem[m.s];
-          const int32_t* __restrict__ ci = f.ci + m.start;
-          const double* __restrict__ cv = f.cv + m.start;
-          double acc = 0.0;
-          for (int e = lane; e < m.nnz; e += 32) {
-            const int j = ci[e];
-            double w, gs;
-            uint32_t lg;
-            ld_state(st + j, w, gs, lg);
-            const uint32_t lagged = t32 - lg;
-            if (lagged != 0) {
-              w = penalty_scalar(pen, w, gs, pen_coef(gamma, beta, ws, lag_scale(identity, f.lag_scaling, lagged)));
-              st_state(st + j, w, gs, t32);
-            }
-            acc += cv[e] * w;
-          }
-          const double dot = warp_sum(acc) * ws;
-          if (lane == 0) {
-            sm.q_dot[sq] = dot;
-            sm.q_ya[sq] = ya;
-            sm.q_gm[sq] = gm;
-            sm.q_s[sq] = m.s;
-            mbar_arrive(&sm.rdy[sq]);
-          }
-          double wcur = ws;
-          if (reset_here) {
-            // Reset(t) over all features, lag = t (src/saga-sparse.h:285-295)
-            __syncwarp();
-            for (int j = lane; j < p; j += 32) {
-              double w, gs;
-              uint32_t lg;
-              ld_state(st + j, w, gs, lg);
-              const uint32_t lagged = t32 - lg;
-              if (lagged != 0)
-                w = penalty_scalar(pen, w, gs, pen_coef(gamma, beta, wcur, lag_scale(identity, f.lag_scaling, lagged)));
-              st_state(st + j, w * wcur, gs, t32);
-            }
-            __syncwarp();
-            wcur = 1.0;
-          }
-          ws_next = wcur * r;
-          const double sc = -gamma / ws_next;
-          const PenCoef pc1 = pen_coef(gamma, beta, ws_next, 1.0);
-          wait_row(sm.gok, q);
-          const double gch = sm.q_gch[sq];
-          for (int e = lane; e < m.nnz; e += 32) {
-            const int j = ci[e];
-            const double gx = cv[e] * gch;
-            double w, gs;
-            uint32_t lg;
-            ld_state(st + j, w, gs, lg);
-            w = w + gx * sc;
-            w = penalty_scalar(pen, w, gs, pc1);
-            st_state(st + j, w, gs + gx * sc2, t32 + 1u);
-          }
-        }
-        // ---- completion: this row's scatter is visible; then the same, chained in row order
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sm.fdone[sq]);
-          if (q > 0) wait_row(sm.done, q - 1);
-          mbar_arrive(&sm.done[sq]);
-        }
-        ws = ws_next;
-        t_sim = t + 1;
+      if (pen == kRidge) {
+        if (ident) wave_worker<S, kRidge, true>(sm, f, k, q_base, warp, lane PROF_PASS);
+        else wave_worker<S, kRidge, false>(sm, f, k, q_base, warp, lane PROF_PASS);
+      } else {
+        if (ident) wave_worker<S, kElasticNet, true>(sm, f, k, q_base, warp, lane PROF_PASS);
+        else wave_worker<S, kElasticNet, false>(sm, f, k, q_base, warp, lane PROF_PASS);
       }
-      // wscale after the epoch's last step (identical in every worker)
-      if (!identity) {
-        while (t_sim < n) {
-          if (ws < kSmall) ws = 1.0;
-          ws *= r;
-          ++t_sim;
-        }
-      }
-      if (tid == 0) sm.wscale_s = ws;
     }
     __syncthreads();
 
     // ---- epoch end: Reset(n), unscale, lag = 0, convergence (src/saga-sparse.h:340-348, 367)
     const double wscale = sm.wscale_s;
+    const double step_e = k.gamma / wscale;
     double mc = 0.0, ms = 0.0;
     for (int j = tid; j < p; j += T) {
       double w, gs;
       uint32_t lg;
-      ld_state(st + j, w, gs, lg);
-      const uint32_t lagged = n32 - lg;
-      if (lagged != 0)
-        w = penalty_scalar(pen, w, gs, pen_coef(gamma, beta, wscale, lag_scale(identity, f.lag_scaling, lagged)));
+      ld_state(k.st + j, w, gs, lg);
+      const uint32_t lagged = n - lg;
+      if (lagged != 0) {
+        const double scal = ident ? static_cast<double>(lagged) : k.ls_table[lagged];
+        const double bgs = k.bg * scal;
+        const double v = w - (step_e * scal) * gs;
+        w = (pen == kElasticNet) ? soft_threshold(v, bgs / wscale) : v;
+      }
       w = w * wscale;
-      st_state(st + j, w, gs, 0u);
+      st_state(k.st + j, w, gs, 0u);
       f.W[j] = w;
       mc = fmax(mc, fabs(w - f.Wprev[j]));
       ms = fmax(ms, fabs(w));
@@ -595,6 +854,10 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
     finished = !free_run && (conv || !(it_outer < f.max_iter));
   }
 
+#ifdef SGD_WAVE_PROF
+  if (lane == 0 && warp < 20)
+    for (int i = 0; i < 8; ++i) g_wave_prof[warp][i] = prof_acc[i];
+#endif
   if (warp == kChain && lane == 0) {
     f.b[0] = b_reg;
     f.gsi[0] = gsi_reg;
@@ -802,11 +1065,20 @@ saga_sparse_generic_kernel(FitDev* __restrict__ fits, Progress* __restrict__ pro
   }
 }
 
+#ifdef SGD_WAVE_PROF
+extern "C" void sgdnet_debug_wave_prof(long long* out) { cudaMemcpyFromSymbol(out, g_wave_prof, sizeof(long long) * 160); }
+extern "C" void sgdnet_debug_wave_path(long long* out) { cudaMemcpyFromSymbol(out, g_wave_path, sizeof(long long) * 12); }
+extern "C" void sgdnet_debug_wave_stall(long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_wave_stall, sizeof(long long) * 32);
+  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(g_wave_stall, z, sizeof(z)); }
+}
+#endif
+
 int wave_warps() {
   static int s = [] {
     int v = 8;
     if (const char* env = std::getenv("SGDNET_WAVE_WARPS")) v = std::atoi(env);
-    return (v == 4 || v == 6 || v == 8 || v == 12) ? v : 8;
+    return (v == 4 || v == 8 || v == 12) ? v : 8;
   }();
   return s;
 }
@@ -838,7 +1110,6 @@ cudaError_t launch_saga_sparse(int n_fits, bool fast_k1, FitDev* fits, Progress*
   if (fast_k1) {
     switch (wave_warps()) {
       case 4: return launch_wave<4>(n_fits, fits, prog, args, st);
-      case 6: return launch_wave<6>(n_fits, fits, prog, args, st);
       case 12: return launch_wave<12>(n_fits, fits, prog, args, st);
       default: return launch_wave<8>(n_fits, fits, prog, args, st);
     }
