@@ -161,11 +161,24 @@ __device__ __forceinline__ double penalty_scalar(int pen, double w, double gs, c
 // sgd_exp for the solver's serial chain: the same operations and the same bits as sgd_exp (include/sgdnet_arith.h),
 // arranged so that arguments whose result is a normal number run straight through (one never-taken branch at the
 // end instead of five early exits); everything else goes to sgd_exp itself.
+static __device__ __noinline__ double sgd_exp_rare(double x) { return sgd_exp(x); }
+// keeps a value in its register: ptxas would otherwise re-derive shared-window addresses (S2UR + ULEA) at every use
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t o;
+  asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(v));
+  return o;
+}
+// returns v through a select on `flag`; `zero` is a run-time zero (FitDev::pad0_) neither nvcc nor ptxas can fold,
+// so the result carries a true data dependence on `flag` that the hardware has to honour
+__device__ __forceinline__ uint32_t dep_on(uint32_t v, bool flag, uint32_t zero) { return flag ? v : v + zero; }
 __device__ __forceinline__ double sgd_exp_inrange(double x) {
   const double kInvStep = 46.16624130844683, kStepHi = 0.021660849392446835, kStepLo = 5.145609244655338e-14;
   const double kShift = 6755399441055744.0;
-  const double kd = fma(x, kInvStep, kShift) - kShift;
-  const int32_t k = static_cast<int32_t>(kd);
+  const double ts = fma(x, kInvStep, kShift);
+  const double kd = ts - kShift;
+  // kd is an integer of magnitude < 2^31 here, and kShift = 1.5 * 2^52 puts it in the low word of ts: the same
+  // value as (int32_t)kd without a conversion on the dependent path
+  const int32_t k = __double2loint(ts);
   double r = fma(-kd, kStepHi, x);
   r = fma(-kd, kStepLo, r);
   double p = 1.0 / 720.0;
@@ -177,8 +190,8 @@ __device__ __forceinline__ double sgd_exp_inrange(double x) {
   const int32_t j = k & 31, m = k >> 5;
   const double thi = sgd_exp_tab_dev[2 * j], tlo = sgd_exp_tab_dev[2 * j + 1];
   const double res = thi + fma(thi, q, tlo);
-  const double out = res * __longlong_as_double(static_cast<long long>(m + 1023) << 52);
-  if (!(x >= -707.0 && x <= 709.0)) return sgd_exp(x);   // also NaN; there m + 1023 may leave [2, 2046]
+  const double out = res * __hiloint2double((m + 1023) << 20, 0);
+  if (__builtin_expect(!(x >= -707.0 && x <= 709.0), 0)) return sgd_exp_rare(x);   // also NaN; m + 1023 may leave [2, 2046]
   return out;
 }
 
@@ -256,6 +269,57 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- the same primitives on 32-bit shared-window addresses (computed once per role, so that the hot loops do not
+// re-derive the shared window base around every access) and with the predicate carried into the instruction
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_if(bool pred, uint32_t a) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pp;\n"
+      "setp.ne.b32 pp, %1, 0;\n"
+      "@pp mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}\n" ::"r"(a),
+      "r"(static_cast<int>(pred))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
 
 // global -> shared bulk copy (UBLKCP in SASS); bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

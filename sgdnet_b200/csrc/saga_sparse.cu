@@ -18,6 +18,7 @@
 // Epoch end (both): Reset(n) over all features by the whole CTA, W *= wscale, lag = 0, convergence test
 // (src/saga-sparse.h:340-348, 367; src/utils.h:240-262).
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -182,12 +183,10 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 // reference performs. Operands outside the safe exponent range (and zero, to keep its sign) take the division.
 __device__ __forceinline__ double div_by_n(double a, double nd, double rn) {
   const double aa = fabs(a);
-  if (aa > 1e-270 && aa < 1e270) {
-    const double q0 = a * rn;
-    const double r0 = fma(-q0, nd, a);
-    return fma(r0, rn, q0);
-  }
-  return a / nd;
+  if (__builtin_expect(!(aa > 1e-270 && aa < 1e270), 0)) return a / nd;
+  const double q0 = a * rn;
+  const double r0 = fma(-q0, nd, a);
+  return fma(r0, rn, q0);
 }
 
 // ---- conflict codes: for every row instance q = epoch*n + t of the staged sequence and every nonzero position e of
@@ -374,33 +373,44 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
   const double nd = k.nd, rn = 1.0 / k.nd, gamma = k.gamma;
   double b_reg = b_io, gsi_reg = gsi_io;
   double* __restrict__ gmem = f.gmem;
+  const bool lead = lane == 0;
+  const uint32_t rt_zero = static_cast<uint32_t>(f.pad0_);   // always 0, but only at run time (see dep_on)
+  // shared-window addresses of the queue rings (8-byte entries; q_s has 4-byte entries)
+  const uint32_t sb = pin_u32(smem_u32(&sm));
+  const uint32_t a_rdy = sb + offsetof(WaveSmem, rdy), a_gok = sb + offsetof(WaveSmem, gok);
+  const uint32_t a_dot = sb + offsetof(WaveSmem, q_dot), a_ya = sb + offsetof(WaveSmem, q_ya);
+  const uint32_t a_gm = sb + offsetof(WaveSmem, q_gm), a_gch = sb + offsetof(WaveSmem, q_gch);
+  const uint32_t a_s = sb + offsetof(WaveSmem, q_s);
   PROF_T(c00);
   wait_row(sm.rdy, q_base);
   PROF_T(c01);
   PROF_ADD(0, c00, c01);
-  double dot = sm.q_dot[q_base % kSeq], ya = sm.q_ya[q_base % kSeq], gm = sm.q_gm[q_base % kSeq];
-  uint32_t s = sm.q_s[q_base % kSeq];
-#pragma unroll 2
+  uint32_t o8 = (q_base % kSeq) * 8u;
+  double dot = lds_f64(a_dot + o8), ya = lds_f64(a_ya + o8), gm = lds_f64(a_gm + o8);
+  uint32_t s = lds_u32(a_s + (o8 >> 1));
+#pragma unroll 4
   for (uint32_t t = 0; t < n; ++t) {
     const uint32_t q = q_base + t;
-    const int sq = static_cast<int>(q % kSeq), sq1 = static_cast<int>((q + 1u) % kSeq);
+    const uint32_t n8 = ((q + 1u) % kSeq) * 8u, par1 = ((q + 1u) / kSeq) & 1u;
     PROF_T(c1);
     // probe the next row's operands while this row's arithmetic runs (non-blocking; the ring has a spare barrier
     // phase, so probing one row past the epoch's end is harmless)
-    const bool next_ready = mbar_test_wait(&sm.rdy[sq1], ((q + 1u) / kSeq) & 1u);
+    const bool next_ready = mbar_test_wait_a(a_rdy + n8, par1);
+    // ... and fetch them behind the probe. The loads' address is made to depend on the probe's result: the barrier
+    // unit and the load/store unit do not order an independent load behind the probe, and a load that overtakes it
+    // can return the previous occupant of the ring slot although the probe then reports "ready".
+    const uint32_t n8d = dep_on(n8, next_ready, rt_zero);
+    double dot_n = lds_f64(a_dot + n8d), ya_n = lds_f64(a_ya + n8d), gm_n = lds_f64(a_gm + n8d);
+    uint32_t s_n = lds_u32(a_s + (n8d >> 1));
     const double lp = dot + b_reg;
     double g;
     if (FAMILY == kBinomial) g = ya - 1.0 / (1.0 + sgd_exp_inrange(lp));   // ya = 1 - y
     else g = lp - ya;
     const double gch = g - gm;
-    if (lane == 0) {
-      sm.q_gch[sq] = gch;
-      gmem[s] = g;
-#ifdef SGD_WAVE_PROF
-      sm.ts_gok[sq] = clock64();
-#endif
-      mbar_arrive(&sm.gok[sq]);
-    }
+    // every lane holds the same values: the stores need no branch, the arrive carries its predicate
+    sts_f64(a_gch + o8, gch);
+    gmem[s] = g;
+    mbar_arrive_if(lead, a_gok + o8);
     if (INTERCEPT) {
       const double gn = div_by_n(gch, nd, rn);
       gsi_reg += gn;
@@ -410,32 +420,25 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
     const long long c2 = (b_reg != 12345.678) ? clock64() : 0;
     PROF_ADD(1, c1, c2);
 #endif
-    if (t + 1u < n) {
-      if (!next_ready) mbar_wait(&sm.rdy[sq1], ((q + 1u) / kSeq) & 1u);
-      dot = sm.q_dot[sq1];
-      ya = sm.q_ya[sq1];
-      gm = sm.q_gm[sq1];
-      s = sm.q_s[sq1];
+    if (__builtin_expect(!next_ready && t + 1u < n, 0)) {
+      mbar_wait_a(a_rdy + n8, par1);
+      dot_n = lds_f64(a_dot + n8);
+      ya_n = lds_f64(a_ya + n8);
+      gm_n = lds_f64(a_gm + n8);
+      s_n = lds_u32(a_s + (n8 >> 1));
     }
+    o8 = n8;
+    dot = dot_n;
+    ya = ya_n;
+    gm = gm_n;
+    s = s_n;
 #ifdef SGD_WAVE_PROF
     const long long c3 = (dot != 12345.678) ? clock64() : 0;
     PROF_ADD(0, c2, c3);
-    if (t + 1u < n && lane == 0) {
-      const uint32_t dm = sm.q_dmin[sq1];
+    if (t + 1u < n && lead) {
+      const uint32_t dm = sm.q_dmin[(q + 1u) % kSeq];
       g_wave_stall[dm][0] += 1;
       g_wave_stall[dm][1] += c3 - c2;
-      if (dm == 1) {   // path of a distance-1 conflict: gok(q) -> gok wake -> fdone(q) -> late wake(q+1) -> rdy(q+1) -> here
-        g_wave_path[0] += 1;
-        g_wave_path[1] += sm.ts_gokwake[sq] - sm.ts_gok[sq];
-        g_wave_path[2] += sm.ts_fdone[sq] - sm.ts_gokwake[sq];
-        g_wave_path[3] += sm.ts_wake[sq1] - sm.ts_fdone[sq];
-        g_wave_path[4] += sm.ts_rdy[sq1] - sm.ts_wake[sq1];
-        g_wave_path[5] += c3 - sm.ts_rdy[sq1];
-        g_wave_path[6] += c3 - sm.ts_gok[sq];
-        g_wave_path[7] += sm.ts_a[sq1] - sm.ts_wake[sq1];
-        g_wave_path[8] += sm.ts_b[sq1] - sm.ts_a[sq1];
-        g_wave_path[9] += sm.ts_rdy[sq1] - sm.ts_b[sq1];
-      }
     }
 #endif
   }
