@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--p", type=int, default=100_000)
     ap.add_argument("--lambda-ind", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the bounded oracle sample")
+    ap.add_argument("--e2e-epochs", type=int, default=16, help="epochs of the bounded sgdnet_fit_sparse call of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -248,7 +249,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         lam = path_lambda(lib, x, y, args.lambda_ind)
-        ne = max(2, args.steps)
+        ne = max(2, args.e2e_epochs)
         ctl2, keep2 = control_for(lib, 1, [lam], maxit=ne)
         ctl2.tol = 0.0
         barrier()

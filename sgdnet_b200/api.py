@@ -368,8 +368,11 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
 
     Deviations, both documented in DESIGN.md: sparse x stays sparse (the reference densifies it,
     :130, quirk Q12), and every fit gets its own generator `set.seed(fit_seeds[k])` (default
-    seed + k, full fits first) so that folds can run concurrently. `shard=(rank, world,
-    gather)` distributes the fold fits over ranks; `gather` all-gathers the per-fit score rows.
+    seed + k, full fits first) so that folds can run concurrently. `shard` (a
+    `sgdnet_b200.shard.Shard`) deals the fold fits to the ranks longest-first; one all_gather of the per-fit score
+    rows ends the run. The #alpha full-data fits run on every rank (concurrently with each other, one CTA each):
+    they supply the lambda paths every rank needs and the fit object every rank returns, and replicating them
+    costs no wall time because a fit occupies one SM.
     """
     lib = backend or _abi.product()
     if type_measure != "deviance":
@@ -411,12 +414,28 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                 standardize_response=kwargs.get("standardize_response", False))
 
     # full-data fits: they supply each alpha's lambda path (R/cv_sgdnet.R:160-164)
-    fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
-            for i, a in enumerate(alphas)]
+    if batched and lib.has("fit_batch_dense"):
+        specs, keeps = [], []
+        for i, a in enumerate(alphas):
+            lmr = opts["lambda_min_ratio"] if opts["lambda_min_ratio"] is not None else (0.01 if n < p else 0.0001)
+            ctl, keep = build_control(family, n_classes, alpha=a, nlambda=opts["nlambda"] if lambdas[i] is None else len(lambdas[i]),
+                                      lambda_min_ratio=lmr, lambda_=lambdas[i], maxit=opts["maxit"],
+                                      standardize=opts["standardize"], intercept=opts["intercept"], thresh=opts["thresh"],
+                                      standardize_response=opts["standardize_response"], debug=False)
+            keeps.append(keep)
+            specs.append(dict(train_rows=None, test_rows=None, control=ctl, rng=lib.rng_from_seed(fit_seeds[i])))
+        raws, _ = lib.fit_batch(x, ymat, specs)
+        fits = [wrap_fit(raw, family, a, class_names, n) for raw, a in zip(raws, alphas)]
+    else:
+        fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
+                for i, a in enumerate(alphas)]
     lambdas = [f.lambda_ for f in fits]
 
-    rank, world, gather = shard if shard is not None else (0, 1, None)
-    mine = [k for k in range(len(plan)) if k % world == rank]
+    if shard is None:
+        from .shard import Shard
+        shard = Shard()
+    costs = [float(len(w["train_rows"])) * len(lambdas[w["alpha_index"]]) for w in plan]
+    mine = shard.mine(costs)
     cv_rows = np.full((len(plan), max(len(l) for l in lambdas)), np.nan)
     fold_fits = [None] * len(plan)
     if batched and lib.has("fit_batch_dense"):
@@ -445,8 +464,7 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                        lambda_=lambdas[w["alpha_index"]], seed=fit_seeds[n_full + k], backend=lib, **opts)
             fold_fits[k] = f
             cv_rows[k, :len(f.lambda_)] = score(f, _rows(x, w["test_rows"]), yarr[w["test_rows"]], "deviance", backend=lib)
-    if gather is not None:
-        cv_rows = gather(cv_rows, mine)
+    cv_rows = shard.all_gather_rows(cv_rows, mine)
 
     cv_raw = []
     for i in range(len(alphas)):

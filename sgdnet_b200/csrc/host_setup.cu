@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace sgd {
 
@@ -15,23 +16,70 @@ void RawX::from_dense(const double* x, int64_t n_, int64_t p_) {
   dense_cm = x;
 }
 
+// Runs body(k, K) on K host threads (K = 1 runs inline). Used only where the result does not depend on K.
+template <typename F>
+static void parallel_blocks(int K, F&& body) {
+  if (K <= 1) {
+    body(0, 1);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(K);
+  for (int k = 0; k < K; ++k) th.emplace_back([&body, k, K] { body(k, K); });
+  for (auto& t : th) t.join();
+}
+
+static int host_threads(int64_t work) {
+  if (work < (int64_t(1) << 22)) return 1;
+  const unsigned hc = std::thread::hardware_concurrency();
+  return static_cast<int>(std::max(1u, std::min(16u, hc)));
+}
+
+// CSC -> CSR (the reference's AdaptiveTranspose, src/utils.h:276-281). Each thread owns a contiguous range of rows
+// and walks every column's (ascending) row-index run restricted to that range, so column ids stay ascending inside
+// every row and the result is the same for any thread count.
 void RawX::from_csc(const int32_t* ci_, const int32_t* cp_, const double* cx_, int64_t n_, int64_t p_) {
   sparse = true;
   n = n_;
   p = static_cast<int32_t>(p_);
   const int64_t nnz = cp_[p_];
   rp.assign(n + 1, 0);
-  for (int64_t e = 0; e < nnz; ++e) ++rp[ci_[e] + 1];
-  for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
   ci.resize(nnz);
   cv.resize(nnz);
-  std::vector<int64_t> cursor(rp.begin(), rp.end() - 1);
-  for (int64_t j = 0; j < p_; ++j)            // ascending j => ascending column ids inside every row
-    for (int64_t e = cp_[j]; e < cp_[j + 1]; ++e) {
-      const int64_t dst = cursor[ci_[e]]++;
-      ci[dst] = static_cast<int32_t>(j);
-      cv[dst] = cx_[e];
+  const int K = host_threads(nnz);
+  auto range_of = [&](int k, int Kt, int64_t& r0, int64_t& r1) {
+    r0 = n * k / Kt;
+    r1 = n * (k + 1) / Kt;
+  };
+  auto span_of = [&](int64_t j, int64_t r0, int64_t r1, int64_t& lo, int64_t& hi, bool whole) {
+    lo = cp_[j];
+    hi = cp_[j + 1];
+    if (whole) return;
+    lo = std::lower_bound(ci_ + lo, ci_ + hi, static_cast<int32_t>(r0)) - ci_;
+    hi = std::lower_bound(ci_ + lo, ci_ + hi, static_cast<int32_t>(r1)) - ci_;
+  };
+  parallel_blocks(K, [&](int k, int Kt) {
+    int64_t r0, r1, lo, hi;
+    range_of(k, Kt, r0, r1);
+    for (int64_t j = 0; j < p_; ++j) {
+      span_of(j, r0, r1, lo, hi, Kt == 1);
+      for (int64_t e = lo; e < hi; ++e) ++rp[ci_[e] + 1];
     }
+  });
+  for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
+  std::vector<int64_t> cursor(rp.begin(), rp.end() - 1);
+  parallel_blocks(K, [&](int k, int Kt) {
+    int64_t r0, r1, lo, hi;
+    range_of(k, Kt, r0, r1);
+    for (int64_t j = 0; j < p_; ++j) {          // ascending j => ascending column ids inside every row
+      span_of(j, r0, r1, lo, hi, Kt == 1);
+      for (int64_t e = lo; e < hi; ++e) {
+        const int64_t dst = cursor[ci_[e]]++;
+        ci[dst] = static_cast<int32_t>(j);
+        cv[dst] = cx_[e];
+      }
+    }
+  });
 }
 
 // ------------------------------------------------------------------------------------------ HostDesign
@@ -100,12 +148,14 @@ void HostDesign::build(const RawX& raw, const int32_t* subset, int64_t n_rows, b
   }
   ci.assign(static_cast<size_t>(cursor) + 4, 0);
   cv.assign(static_cast<size_t>(cursor) + 4, 0.0);
-  for (int64_t i = 0; i < n; ++i) {
-    const int64_t r = src_row(i);
-    const int64_t b = raw.rp[r];
-    std::memcpy(&ci[rows[i].start], &raw.ci[b], sizeof(int32_t) * rows[i].nnz);
-    std::memcpy(&cv[rows[i].start], &raw.cv[b], sizeof(double) * rows[i].nnz);
-  }
+  parallel_blocks(host_threads(cursor), [&](int k, int Kt) {
+    for (int64_t i = n * k / Kt; i < n * (k + 1) / Kt; ++i) {
+      const int64_t r = src_row(i);
+      const int64_t b = raw.rp[r];
+      std::memcpy(&ci[rows[i].start], &raw.ci[b], sizeof(int32_t) * rows[i].nnz);
+      std::memcpy(&cv[rows[i].start], &raw.cv[b], sizeof(double) * rows[i].nnz);
+    }
+  });
   if (standardize) {
     // sparse Mean / StandardDeviation (src/math.h:66-79, 89-112): per-column running sums in ascending row order;
     // then scale only (src/utils.h:118-120), centring stays virtual through c = center/scale (src/sgdnet.cpp:150)
