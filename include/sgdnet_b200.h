@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SGDNET_ABI_VERSION 1
+#define SGDNET_ABI_VERSION 2
 
 /* status codes */
 #define SGDNET_OK            0
@@ -173,6 +173,10 @@ typedef struct sgdnet_fit_spec {
   int64_t        n_train;
   const int32_t* test_rows;    /* rows scored after the fit; NULL/0 => no score                */
   int64_t        n_test;
+  int32_t        lambda_from;  /* -1, or the index of an EARLIER spec of the batch whose lambda path (automatic or
+                                  given) this fit uses: `lambda = lambda[[i]]` of R/cv_sgdnet.R:164, 186, known after
+                                  that fit's setup, so full fits and their fold fits can share one batch      */
+  int32_t        pad_;
   sgdnet_control control;
   sgdnet_rng     rng;
 } sgdnet_fit_spec;

@@ -1,0 +1,37 @@
+"""BASELINE config 5 on one GPU: 10-fold cv_sgdnet x 5-alpha grid, binomial sparse (default n = 500k, p = 50k, 50 nnz/row),
+every fit one CTA, all fits of a phase concurrent. Prints fits/s and aggregate sample-updates/s.
+Usage: python scripts/cv_bench.py [n] [p] [nlambda] [maxit]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sgdnet_b200 as sg
+from sgdnet_b200 import synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
+p = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000
+nlambda = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+maxit = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+x, y = synth.binomial_sparse(n, p, 50, seed=1005)
+perm = np.random.Generator(np.random.PCG64(1005)).permutation(n)
+foldid = (perm % 10) + 1
+lib = sg.product()
+t0 = time.perf_counter()
+cv = sg.cv_sgdnet(x, y, family="binomial", alpha=[0.0, 0.25, 0.5, 0.75, 1.0], foldid=foldid, nlambda=nlambda,
+                  standardize=False, maxit=maxit, seed=1000, backend=lib)
+wall = time.perf_counter() - t0
+upd_full = sum(int(f.npasses) * n for f in cv.fits)
+upd_fold = sum(int(f.npasses) * f.nobs for f in cv.fold_fits)
+solver_full = max(f.raw.seconds_solver for f in cv.fits)
+solver_fold = max(f.raw.seconds_solver for f in cv.fold_fits)
+print(json.dumps({"workload": f"cv_sgdnet 10 folds x 5 alphas, binomial sparse {n}x{p}, 50 nnz/row, nlambda={nlambda}, maxit={maxit}",
+                  "fits": len(cv.fits) + len(cv.fold_fits), "wall_s": wall, "fits_per_s": (len(cv.fits) + len(cv.fold_fits)) / wall,
+                  "updates_full_fits": upd_full, "updates_fold_fits": upd_fold,
+                  "solver_s_full_phase": solver_full, "solver_s_fold_phase": solver_fold,
+                  "agg_updates_per_s_fold_phase": upd_fold / solver_fold, "agg_updates_per_s_full_phase": upd_full / solver_full,
+                  "alpha_min": cv.alpha_min, "lambda_min": cv.lambda_min}))

@@ -91,6 +91,8 @@ class FitSpec(C.Structure):
         ("n_train", C.c_int64),
         ("test_rows", c_int32_p),
         ("n_test", C.c_int64),
+        ("lambda_from", C.c_int32),
+        ("pad_", C.c_int32),
         ("control", Control),
         ("rng", Rng),
     ]
@@ -328,6 +330,7 @@ class Library:
             if te is not None and len(te) > 0:
                 te = np.ascontiguousarray(te, dtype=np.int32); keep.append(te)
                 arr[i].test_rows = _ptr(te, c_int32_p); arr[i].n_test = te.size
+            arr[i].lambda_from = int(s.get("lambda_from", -1))
             arr[i].control = s["control"]
             arr[i].rng = s["rng"]
             n_lambda = max(n_lambda, s["control"].n_lambda)

@@ -413,50 +413,48 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                 intercept=kwargs.get("intercept", True), thresh=kwargs.get("thresh", 0.001),
                 standardize_response=kwargs.get("standardize_response", False))
 
-    # full-data fits: they supply each alpha's lambda path (R/cv_sgdnet.R:160-164)
-    if batched and lib.has("fit_batch_dense"):
-        specs, keeps = [], []
-        for i, a in enumerate(alphas):
-            lmr = opts["lambda_min_ratio"] if opts["lambda_min_ratio"] is not None else (0.01 if n < p else 0.0001)
-            ctl, keep = build_control(family, n_classes, alpha=a, nlambda=opts["nlambda"] if lambdas[i] is None else len(lambdas[i]),
-                                      lambda_min_ratio=lmr, lambda_=lambdas[i], maxit=opts["maxit"],
-                                      standardize=opts["standardize"], intercept=opts["intercept"], thresh=opts["thresh"],
-                                      standardize_response=opts["standardize_response"], debug=False)
-            keeps.append(keep)
-            specs.append(dict(train_rows=None, test_rows=None, control=ctl, rng=lib.rng_from_seed(fit_seeds[i])))
-        raws, _ = lib.fit_batch(x, ymat, specs)
-        fits = [wrap_fit(raw, family, a, class_names, n) for raw, a in zip(raws, alphas)]
-    else:
-        fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
-                for i, a in enumerate(alphas)]
-    lambdas = [f.lambda_ for f in fits]
-
     if shard is None:
         from .shard import Shard
         shard = Shard()
-    costs = [float(len(w["train_rows"])) * len(lambdas[w["alpha_index"]]) for w in plan]
-    mine = shard.mine(costs)
-    cv_rows = np.full((len(plan), max(len(l) for l in lambdas)), np.nan)
+    plan_costs = [float(len(w["train_rows"])) for w in plan]
+    mine = shard.mine(plan_costs)
+    cv_rows = np.full((len(plan), opts["nlambda"] if lambdas[0] is None else max(len(l) for l in lambdas)), np.nan)
     fold_fits = [None] * len(plan)
+
+    def control_for(a, lam, n_rows):
+        lmr = opts["lambda_min_ratio"] if opts["lambda_min_ratio"] is not None else (0.01 if n_rows < p else 0.0001)
+        return build_control(family, n_classes, alpha=a, nlambda=opts["nlambda"] if lam is None else len(lam),
+                             lambda_min_ratio=lmr, lambda_=lam, maxit=opts["maxit"], standardize=opts["standardize"],
+                             intercept=opts["intercept"], thresh=opts["thresh"],
+                             standardize_response=opts["standardize_response"], debug=False)
+
     if batched and lib.has("fit_batch_dense"):
+        # ONE batch: the full-data fits (they supply each alpha's lambda path, R/cv_sgdnet.R:160-164) and this rank's
+        # fold fits, which take that path through `lambda_from` - it is known after the full fit's setup, so all the
+        # fits run concurrently, one CTA each
         specs, keeps = [], []
+        for i, a in enumerate(alphas):
+            ctl, keep = control_for(a, lambdas[i], n)
+            keeps.append(keep)
+            specs.append(dict(train_rows=None, test_rows=None, control=ctl, rng=lib.rng_from_seed(fit_seeds[i])))
         for k in mine:
             w = plan[k]
-            n_tr = len(w["train_rows"])
-            lmr = opts["lambda_min_ratio"] if opts["lambda_min_ratio"] is not None else (0.01 if n_tr < p else 0.0001)
-            ctl, keep = build_control(family, n_classes, alpha=w["alpha"], nlambda=len(lambdas[w["alpha_index"]]),
-                                      lambda_min_ratio=lmr, lambda_=lambdas[w["alpha_index"]], maxit=opts["maxit"],
-                                      standardize=opts["standardize"], intercept=opts["intercept"], thresh=opts["thresh"],
-                                      standardize_response=opts["standardize_response"], debug=False)
+            ctl, keep = control_for(w["alpha"], lambdas[w["alpha_index"]], len(w["train_rows"]))
             keeps.append(keep)
             specs.append(dict(train_rows=w["train_rows"], test_rows=w["test_rows"], control=ctl,
-                              rng=lib.rng_from_seed(fit_seeds[n_full + k])))
-        if specs:
-            raws, scores = lib.fit_batch(x, ymat, specs)
-            for k, raw, sc in zip(mine, raws, scores):
-                fold_fits[k] = wrap_fit(raw, family, plan[k]["alpha"], class_names, len(plan[k]["train_rows"]))
-                cv_rows[k, :len(raw.lambda_)] = sc[:len(raw.lambda_)]
+                              rng=lib.rng_from_seed(fit_seeds[n_full + k]),
+                              lambda_from=w["alpha_index"] if lambdas[w["alpha_index"]] is None else -1))
+        raws, scores = lib.fit_batch(x, ymat, specs)
+        fits = [wrap_fit(raw, family, a, class_names, n) for raw, a in zip(raws[:n_full], alphas)]
+        lambdas = [f.lambda_ for f in fits]
+        for k, raw, sc in zip(mine, raws[n_full:], scores[n_full:]):
+            fold_fits[k] = wrap_fit(raw, family, plan[k]["alpha"], class_names, len(plan[k]["train_rows"]))
+            cv_rows[k, :len(raw.lambda_)] = sc[:len(raw.lambda_)]
     else:
+        fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
+                for i, a in enumerate(alphas)]
+        lambdas = [f.lambda_ for f in fits]
+        cv_rows = np.full((len(plan), max(len(l) for l in lambdas)), np.nan)
         yarr = np.asarray(y)
         for k in mine:
             w = plan[k]

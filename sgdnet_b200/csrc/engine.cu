@@ -584,7 +584,7 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
       if (!xa.sparse) return s.control.n_classes == 1 ? 0 : 1;
       return (s.control.n_classes == 1 && !s.control.standardize) ? 2 : 3;
     };
-    int max_lambda = 0;
+    int max_lambda = 0;      // row stride of `scores`: the caller sizes it from the controls it passed
     for (int i = 0; i < n_fits; ++i) max_lambda = std::max(max_lambda, specs[i].control.n_lambda);
     for (int v = 0; v < 4; ++v) {
       std::vector<int> group;
@@ -593,10 +593,23 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
       if (group.empty()) continue;
       Engine eng;
       load_x(eng, xa, y, y_cols);
+      std::map<int, int> job_of;   // spec index -> job index inside this engine
       for (int i : group) {
         sgdnet_fit_spec& s = specs[i];
-        std::string err = eng.add_fit(s.train_rows, s.n_train, s.control, &s.rng, s.test_rows, s.n_test);
+        sgdnet_control ctl = s.control;
+        if (s.lambda_from >= 0) {
+          // lambda = the path of an earlier fit of the batch (R/cv_sgdnet.R:164, 186), known after that fit's setup
+          auto src = job_of.find(s.lambda_from);
+          if (s.lambda_from >= i || src == job_of.end())
+            return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": lambda_from must name an earlier fit of the same kind");
+          const std::vector<double>& lam = eng.jobs[src->second].plan.lambda;
+          ctl.lambda = lam.data();
+          ctl.lambda_len = static_cast<int32_t>(lam.size());
+          ctl.n_lambda = ctl.lambda_len;
+        }
+        std::string err = eng.add_fit(s.train_rows, s.n_train, ctl, &s.rng, s.test_rows, s.n_test);
         if (!err.empty()) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + err);
+        job_of[i] = static_cast<int>(eng.jobs.size()) - 1;
       }
       eng.finalize_batch();
       eng.run();

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib.lib, n), n
-    assert lib.lib.sgdnet_abi_version() == 1
+    assert lib.lib.sgdnet_abi_version() == 2
 
 
 def test_struct_sizes_match_the_header():

@@ -79,6 +79,28 @@ def test_sparse_k1_synthetic(cuda, oracle, family, alpha, intercept):
     assert_fit_parity(g.raw, r.raw)
 
 
+@pytest.mark.parametrize("family,alpha,intercept", [("binomial", 1.0, True), ("binomial", 0.4, True), ("gaussian", 0.0, True),
+                                                    ("gaussian", 1.0, False), ("binomial", 0.0, False)])
+def test_sparse_wavefront_stress(cuda, oracle, family, alpha, intercept):
+    """Many rows in flight with frequent feature conflicts (10 % per row pair), forwarding chains and, for alpha < 1,
+    wscale resets inside epochs: the overlapped schedule must leave every coefficient bit-identical."""
+    x, yb = synth.binomial_sparse(8000, 1000, 10, seed=41)
+    y = yb if family == "binomial" else (x @ np.linspace(-2, 2, 1000) + 0.3 * yb)
+    g, r = both(cuda, oracle, x, y, family=family, alpha=alpha, intercept=intercept, standardize=False,
+                nlambda=6, thresh=1e-3, maxit=40, seed=12)
+    assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_sparse_wavefront_dense_conflicts_and_repeated_samples(cuda, oracle, alpha):
+    """Tiny p and n: almost every row shares features with its predecessors and the same sample recurs inside the
+    window of rows in flight (gradient-memory hazard)."""
+    x, y = synth.binomial_sparse(120, 48, 8, seed=43)
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=alpha, standardize=False, nlambda=8, thresh=1e-5,
+                maxit=200, seed=13)
+    assert_fit_parity(g.raw, r.raw)
+
+
 def test_sparse_long_and_empty_rows(cuda, oracle):
     """Rows longer than a ring slot (> 128 nonzeros) and empty rows take the in-place path."""
     rng = np.random.Generator(np.random.PCG64(5))
