@@ -77,7 +77,7 @@ struct FitDev {
   // ---- scratch
   double *partials;          // per-block partial sums for the grid-wide passes
   int32_t debug;
-  int32_t pad0_;
+  int32_t pad0_;             // always 0 (read as a run-time zero, see dep_on)
 };
 
 // Device-updated progress of one fit; read back by the host after every round.
@@ -103,8 +103,14 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// SoftThreshold (src/prox.h:32-39): max(x - s, 0) - max(-x - s, 0) for a threshold s >= 0. Evaluated as
+// t = |x| - s; t <= 0 ? +0 : copysign(t, x) - the same value bit for bit (IEEE rounding is symmetric, so
+// RN(|x| - s) = |RN(x -+ s)|; the side that is clamped contributes an exact +0; a NaN stays a NaN as with
+// std::max), in a third of the instructions (an FP64 max is a compare-and-select sequence).
+// tests/test_arith_cpu.py checks the identity against the reference form.
 __device__ __forceinline__ double soft_threshold(double x, double s) {
-  return fmax(x - s, 0.0) - fmax(-x - s, 0.0);
+  const double t = fabs(x) - s;
+  return (t <= 0.0) ? 0.0 : copysign(t, x);
 }
 
 // The three scalars a penalty functor derives from (gamma, beta, w_scale, scaling); computed once per call site with
@@ -203,6 +209,22 @@ __device__ __forceinline__ double gradient_scalar(int family, double lp, double 
 __device__ __forceinline__ double loss_scalar(int family, double lp, double y) {
   if (family == kBinomial) return sgd_log(1.0 + sgd_exp(lp)) - y * lp;
   return 0.5 * (lp - y) * (lp - y);
+}
+
+// a / n with n an integer below 2^32: q = a*(1/n) corrected once with the exact residual is the correctly rounded
+// quotient (the residual step leaves a relative error of 2^-104 while a/n stays 2^-86 away from every rounding
+// boundary because n has at most 32 significant bits), so this returns the same bits as the IEEE division the
+// reference performs. Zero is returned as it is (keeps its sign); operands outside the safe exponent range take
+// the division.
+__device__ __forceinline__ double div_by_n(double a, double nd, double rn) {
+  // safe when the biased exponent is in [127, 1919] (|a| in [2^-896, 2^897)): integer test on the high word
+  const uint32_t ex = (static_cast<uint32_t>(__double2hiint(a)) >> 20) & 0x7ffu;
+  const bool ok = (ex - 127u) <= 1792u;
+  if (__builtin_expect(!ok && a != 0.0, 0)) return a / nd;
+  const double q0 = a * rn;
+  const double r0 = fma(-q0, nd, a);
+  const double q1 = fma(r0, rn, q0);
+  return ok ? q1 : a;       // a == +-0 here
 }
 
 // ---- families, K-vector held one class per lane of a warp (K <= 32 per call chunk is handled by callers through

@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sgdnet_b200.h"
@@ -127,6 +128,7 @@ struct Engine {
   int sms = 148;
   int64_t max_rows_per_launch = 1;
   size_t dense_smem = 0;
+  unsigned dense_kts = 0, dense_pens = 0;   // class-count buckets / penalties present (dense kernel instantiations)
   Variant variant = Variant::Dense;
   bool any_debug = false;
   uint64_t launches = 0;
@@ -282,6 +284,10 @@ struct Engine {
     if (variant == Variant::Dense) {
       int in_smem = 0;
       dense_smem = dense_smem_bytes(max_K, max_p, max_ld, &in_smem);
+      for (auto& j : jobs) {
+        dense_kts |= static_cast<unsigned>(dense_kt_bucket(j.dev.K));
+        dense_pens |= 1u << j.dev.penalty;
+      }
     }
     // streaming passes: enough CTAs to fill the GPU across the fits of the batch, at least one per fit
     int dev_id = 0;
@@ -306,24 +312,61 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------------------------- index stream
+  // Makes sure `need` undrawn-by-the-device indices are pending (host memory). May run on a helper thread while the
+  // device works: it touches only this job's generator and buffers.
+  bool ensure_pending(FitJob& j, size_t need) {
+    size_t have = j.pending.size() - j.pending_head;
+    if (have >= need) return true;
+    if (j.pending_head > 0) {
+      j.pending.erase(j.pending.begin(), j.pending.begin() + j.pending_head);
+      j.pending_head = 0;
+    }
+    const size_t add = need - have;
+    j.marks.emplace_back(j.generated, *j.rng);
+    if (j.marks.size() > 8) j.marks.erase(j.marks.begin());
+    const size_t old = j.pending.size();
+    j.pending.resize(old + add);
+    if (!draw_indices(j.rng, static_cast<uint32_t>(j.dev.n), static_cast<int64_t>(add), j.pending.data() + old)) return false;
+    j.generated += add;
+    return true;
+  }
+
   bool stage_indices(FitJob& j, int n_epochs) {
     const size_t need = size_t(n_epochs) * j.dev.n;
-    size_t have = j.pending.size() - j.pending_head;
-    if (have < need) {
-      if (j.pending_head > 0) {
-        j.pending.erase(j.pending.begin(), j.pending.begin() + j.pending_head);
-        j.pending_head = 0;
-      }
-      const size_t add = need - have;
-      j.marks.emplace_back(j.generated, *j.rng);
-      if (j.marks.size() > 4) j.marks.erase(j.marks.begin());
-      const size_t old = j.pending.size();
-      j.pending.resize(old + add);
-      if (!draw_indices(j.rng, static_cast<uint32_t>(j.dev.n), static_cast<int64_t>(add), j.pending.data() + old)) return false;
-      j.generated += add;
-    }
+    if (!ensure_pending(j, need)) return false;
     std::memcpy(j.seq_pin, j.pending.data() + j.pending_head, need * sizeof(uint32_t));
     return true;
+  }
+
+  // While the device runs a round: draw the next round's indices for every fit that may need them (a fit consumes
+  // at most one launch's worth per round), spread over host threads. The callback generator is never drawn ahead
+  // (it must be called on the caller's thread, exactly as often as the reference would call it).
+  void prefetch_indices() {
+    std::vector<FitJob*> todo;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      FitJob& j = jobs[i];
+      if (j.done || args_host[i].n_epochs == 0 || j.rng->kind == SGDNET_RNG_CALLBACK) continue;
+      if (j.rng->kind == SGDNET_RNG_SEQUENCE &&
+          j.rng->seq_len - j.rng->seq_pos < static_cast<int64_t>(2 * size_t(j.epochs_per_launch) * j.dev.n)) continue;
+      todo.push_back(&j);
+    }
+    if (todo.empty()) return;
+    const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int K = static_cast<int>(std::min<size_t>(hc, todo.size()));
+    auto work = [&](int k) {
+      for (size_t q = k; q < todo.size(); q += K) {
+        FitJob& j = *todo[q];
+        (void)ensure_pending(j, 2 * size_t(j.epochs_per_launch) * j.dev.n);
+      }
+    };
+    if (K == 1) {
+      work(0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto& t : th) t.join();
   }
 
   // Give the caller's generator back advanced by exactly the draws the fit consumed.
@@ -382,7 +425,7 @@ struct Engine {
         ++launches;
       }
       if (variant == Variant::Dense)
-        CK(launch_saga_dense(nf, jobs[0].dev.K == 1, dense_smem, fits_dev, prog_dev, args_dev, stream));
+        CK(launch_saga_dense(nf, dense_kts, dense_pens, dense_smem, fits_dev, prog_dev, args_dev, stream));
       else
         CK(launch_saga_sparse(nf, variant == Variant::SparseK1, fits_dev, prog_dev, args_dev, stream));
       ++launches;
@@ -395,6 +438,7 @@ struct Engine {
       launches += 2;
       CK(cudaEventRecord(ev2, stream));
       CK(cudaMemcpyAsync(prog_host, prog_dev, sizeof(Progress) * nf, cudaMemcpyDeviceToHost, stream));
+      prefetch_indices();
       CK(cudaStreamSynchronize(stream));
       float ms_solver = 0.f, ms_dev = 0.f;
       CK(cudaEventElapsedTime(&ms_solver, ev0, ev1));
@@ -818,7 +862,7 @@ int sgdnet_session_run_epochs(sgdnet_session* s, int32_t lambda_ind, int32_t n_e
         ++e.launches;
       }
       if (e.variant == Variant::Dense)
-        CK(launch_saga_dense(1, j.dev.K == 1, e.dense_smem, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
+        CK(launch_saga_dense(1, e.dense_kts, e.dense_pens, e.dense_smem, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
       else
         CK(launch_saga_sparse(1, e.variant == Variant::SparseK1, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
       ++e.launches;

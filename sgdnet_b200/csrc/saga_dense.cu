@@ -63,22 +63,28 @@ size_t dense_smem_bytes(int K, int p, int ld, int* state_in_smem) {
   return fixed;
 }
 
-template <bool kScalar>
+// KT: number of classes rounded up to 1 (K == 1: gaussian / binomial), 4, 8, 16 or 32; PEN: the penalty functor.
+// Both are compile-time so that the per-class loops unroll: the KT dot-product butterflies of a warp then run
+// interleaved (one butterfly's latency instead of K of them) and the coefficient sweep is straight-line code.
+template <int KT, int PEN>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const RoundArgs* __restrict__ args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool kScalar = (KT == 1);
   const int fit_id = blockIdx.x;
   const RoundArgs ra = args[fit_id];
   Progress& pg = prog[fit_id];
   if (ra.n_epochs <= 0 || pg.status != kRunning) return;
-  const bool free_run = (ra.flags & 1) != 0;
   const FitDev& f = fits[fit_id];
+  if (f.penalty != PEN || (kScalar ? f.K != 1 : (f.K <= KT / 2 && KT > 4) || f.K > KT || f.K == 1)) return;   // another instantiation's fit
+  const bool free_run = (ra.flags & 1) != 0;
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int K = kScalar ? 1 : f.K, p = f.p, ld = f.ld, Ky = f.Ky;
   const int64_t n = f.n;
   const double nd = static_cast<double>(static_cast<uint32_t>(n));
-  const int family = f.family, pen = f.penalty;
+  const double rn = 1.0 / nd;
+  const int family = f.family;
   const bool fit_intercept = f.fit_intercept != 0;
 
   int state_in_smem;
@@ -131,43 +137,65 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
   uint32_t it_outer = pg.it_outer;
   uint32_t epochs_done = 0;
   int64_t tg = 0;                            // global update counter within this launch
-  uint32_t prev_s = 0xffffffffu;
-  double prev_g = 0.0;
+  uint32_t prev_s = 0xffffffffu, prev2_s = 0xffffffffu;
+  double prev_g = 0.0, prev2_g = 0.0;
   bool finished = false;
+
+  // Per-sample operands (index, y, gradient memory) are fetched ONE UPDATE AHEAD so that their HBM latency never sits
+  // on the gradient step. A gradient-memory value fetched that early can be stale for the last two samples (their
+  // stores are not ordered before the fetch), so those are forwarded from registers instead.
+  const bool owner = kScalar || (warp == 0 && lane < K);
+  auto fetch_y = [&](uint32_t sx) { return kScalar ? f.yt[sx] : f.yt[size_t(sx) * Ky + (Ky == 1 ? 0 : lane)]; };
+  auto fetch_gm = [&](uint32_t sx) { return kScalar ? f.gmem[sx] : f.gmem[size_t(sx) * K + lane]; };
+  uint32_t s_cur = seq[0], s_nxt = (total > 1) ? seq[1] : 0u;
+  double y_cur = 0.0, gm_cur = 0.0;
+  if (owner) {
+    y_cur = fetch_y(s_cur);
+    gm_cur = fetch_gm(s_cur);
+  }
+  uint32_t s_refill = (tid == 0 && issued < total) ? seq[issued] : 0u;   // sample of the next row copy (thread 0)
 
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep) {
     for (int64_t t = 0; t < n; ++t, ++tg) {
-      const uint32_t s = seq[tg];
+      const uint32_t s = s_cur;
       const int slot = static_cast<int>(tg % kRing);
       const uint32_t parity = static_cast<uint32_t>((tg / kRing) & 1);
-
-      // small per-sample operands, issued before the wait so their latency overlaps the dot product
-      double y_val = 0.0, gm_val = 0.0;
-      if (kScalar) {
-        y_val = f.yt[s];
-        gm_val = (s == prev_s) ? prev_g : f.gmem[s];   // the previous update's store may still be in flight
-      } else if (warp == 0 && lane < K) {
-        y_val = f.yt[size_t(s) * Ky + (Ky == 1 ? 0 : lane)];
-        gm_val = f.gmem[size_t(s) * K + lane];
+      const double y_val = y_cur;
+      const double gm_val = (s == prev_s) ? prev_g : ((s == prev2_s) ? prev2_g : gm_cur);
+      // next update's operands
+      s_cur = s_nxt;
+      if (tg + 2 < total) s_nxt = seq[tg + 2];
+      if (owner && tg + 1 < total) {
+        y_cur = fetch_y(s_cur);
+        gm_cur = fetch_gm(s_cur);
       }
 
       mbar_wait(&sm.full[slot], parity);
       const double* __restrict__ xr = sm.ring + size_t(slot) * ld;
       double* red = sm.red + size_t(tg & 1) * nwarps * K;   // step B of update t may still be reading the other half
 
-      // ---- A: dot products
-      if (kScalar) {
-        double acc = 0.0;
-        for (int j = tid; j < p; j += T) acc += W[j] * xr[j];
-        acc = warp_sum(acc);
-        if (lane == 0) red[warp] = acc;
-      } else {
-        for (int k = 0; k < K; ++k) {
-          double acc = 0.0;
-          const double* Wk = W + size_t(k) * p;
-          for (int j = tid; j < p; j += T) acc += Wk[j] * xr[j];
-          acc = warp_sum(acc);
-          if (lane == 0) red[warp * K + k] = acc;
+      // ---- A: dot products. Thread tid owns the running sums of features j = tid (mod 256) for every class; the
+      // warp's KT butterflies are independent and interleave (sgdnet_arith.h, item 2).
+      {
+        double acc[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+        for (int j = tid; j < p; j += T) {
+          const double xj = xr[j];
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (kScalar || k < K) acc[k] += W[size_t(k) * p + j] * xj;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (kScalar || k < K) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (kScalar || k < K) red[warp * K + k] = acc[k];
         }
       }
       __syncthreads();   // (1) partial sums visible; every thread is past step C of the previous update
@@ -175,8 +203,9 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
       if (tid == 0 && issued < total) {      // refill the slot the previous update just released
         const int fslot = static_cast<int>(issued % kRing);
         mbar_expect_tx(&sm.full[fslot], row_bytes);
-        bulk_g2s(sm.ring + size_t(fslot) * ld, f.xd + size_t(seq[issued]) * ld, row_bytes, &sm.full[fslot]);
+        bulk_g2s(sm.ring + size_t(fslot) * ld, f.xd + size_t(s_refill) * ld, row_bytes, &sm.full[fslot]);
         ++issued;
+        if (issued < total) s_refill = seq[issued];
       }
 
       // ---- B: gradient, gradient memory, intercept
@@ -188,6 +217,10 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
         const double g = gradient_scalar(family, lp, y_val);
         gch_scalar = g - gm_val;
         if (tid == 0) f.gmem[s] = g;
+        if (s != prev_s) {
+          prev2_s = prev_s;
+          prev2_g = prev_g;
+        }
         prev_s = s;
         prev_g = g;
         if (wscale < kSmall) {
@@ -196,8 +229,9 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
         }
         wscale *= r;
         if (fit_intercept) {
-          gsi_reg += gch_scalar / nd;
-          b_reg -= gamma * (gsi_reg + gch_scalar / nd);
+          const double gn = div_by_n(gch_scalar, nd, rn);
+          gsi_reg += gn;
+          b_reg -= gamma * (gsi_reg + gn);
         }
       } else {
         if (warp == 0) {
@@ -222,11 +256,18 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
             const double gch = g - gm_val;
             f.gmem[size_t(s) * K + lane] = g;
             if (fit_intercept) {
-              gsi_reg += gch / nd;
-              b_reg -= gamma * (gsi_reg + gch / nd);
+              const double gn = div_by_n(gch, nd, rn);
+              gsi_reg += gn;
+              b_reg -= gamma * (gsi_reg + gn);
             }
             sm.gch[lane] = gch;
           }
+          if (s != prev_s) {
+            prev2_s = prev_s;
+            prev2_g = prev_g;
+          }
+          prev_s = s;
+          prev_g = g;
         }
         if (wscale < kSmall) {
           for (int j = tid; j < p; j += T)
@@ -238,24 +279,39 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
       }
 
       // ---- C: fused coefficient step, prox, gradient-average update on the owned features
+      // (src/saga-dense.h:176-183; penalty functors src/penalties.h:27-79 with scaling = 1)
       const double gw = gamma / wscale;
-      const PenCoef pc = pen_coef(gamma, beta, wscale, 1.0);
-      if (kScalar) {
-        for (int j = tid; j < p; j += T) {
-          const double xj = xr[j];
-          const double gx = gch_scalar * xj;
-          const double gs = G[j];
-          double w = W[j] - gx * gw;
-          W[j] = penalty_scalar(pen, w, gs, pc);
-          G[j] = gs + gx / nd;
+      const double step = gamma / wscale * 1.0;
+      const double bgs = beta * gamma * 1.0;
+      const double thr = bgs / wscale;
+      double gch[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) gch[k] = kScalar ? gch_scalar : ((k < K) ? sm.gch[k] : 0.0);
+      for (int j = tid; j < p; j += T) {
+        const double xj = xr[j];
+        double w[KT], gs[KT];
+        double sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (kScalar || k < K) {
+            gs[k] = G[size_t(k) * p + j];
+            const double gx = gch[k] * xj;
+            const double v = (W[size_t(k) * p + j] - gx * gw) - step * gs[k];
+            w[k] = (PEN == kElasticNet) ? soft_threshold(v, thr) : v;
+            if (PEN == kGroupLasso) sq += v * v;
+            G[size_t(k) * p + j] = gs[k] + div_by_n(gx, nd, rn);
+          }
         }
-      } else {
-        for (int j = tid; j < p; j += T) {
-          const double xj = xr[j];
-          for (int k = 0; k < K; ++k) W[size_t(k) * p + j] -= sm.gch[k] * xj * gw;
-          apply_penalty(pen, W + j, G + j, K, p, pc);
-          for (int k = 0; k < K; ++k) G[size_t(k) * p + j] += sm.gch[k] * xj / nd;
+        if (PEN == kGroupLasso) {
+          const double factor = bgs / sqrt(sq);
+          const double mult = 1.0 - factor / wscale;
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (kScalar || k < K) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (kScalar || k < K) W[size_t(k) * p + j] = w[k];
       }
     }
 
@@ -322,21 +378,42 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
   }
 }
 
-cudaError_t launch_saga_dense(int n_fits, bool scalar, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
-                              cudaStream_t st) {
+template <int KT, int PEN>
+static cudaError_t launch_dense_variant(int n_fits, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
+                                        cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(saga_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(saga_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(saga_dense_kernel<KT, PEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (scalar)
-    saga_dense_kernel<true><<<n_fits, kDenseThreads, smem, st>>>(fits, prog, args);
-  else
-    saga_dense_kernel<false><<<n_fits, kDenseThreads, smem, st>>>(fits, prog, args);
+  saga_dense_kernel<KT, PEN><<<n_fits, kDenseThreads, smem, st>>>(fits, prog, args);
   return cudaGetLastError();
 }
+
+template <int KT>
+static cudaError_t launch_dense_kt(unsigned pens, int n_fits, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
+                                   cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if ((pens & (1u << kRidge)) && e == cudaSuccess) e = launch_dense_variant<KT, kRidge>(n_fits, smem, fits, prog, args, st);
+  if ((pens & (1u << kElasticNet)) && e == cudaSuccess) e = launch_dense_variant<KT, kElasticNet>(n_fits, smem, fits, prog, args, st);
+  if ((pens & (1u << kGroupLasso)) && e == cudaSuccess) e = launch_dense_variant<KT, kGroupLasso>(n_fits, smem, fits, prog, args, st);
+  return e;
+}
+
+// One launch per (class-count bucket, penalty) present in the batch; a CTA whose fit belongs to another
+// instantiation returns at once. `kts` / `pens`: bit masks of the buckets (the bucket value itself) and penalties present.
+cudaError_t launch_saga_dense(int n_fits, unsigned kts, unsigned pens, size_t smem, FitDev* fits, Progress* prog,
+                              const RoundArgs* args, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if ((kts & 1u) && e == cudaSuccess) e = launch_dense_kt<1>(pens, n_fits, smem, fits, prog, args, st);
+  if ((kts & 4u) && e == cudaSuccess) e = launch_dense_kt<4>(pens, n_fits, smem, fits, prog, args, st);
+  if ((kts & 8u) && e == cudaSuccess) e = launch_dense_kt<8>(pens, n_fits, smem, fits, prog, args, st);
+  if ((kts & 16u) && e == cudaSuccess) e = launch_dense_kt<16>(pens, n_fits, smem, fits, prog, args, st);
+  if ((kts & 32u) && e == cudaSuccess) e = launch_dense_kt<32>(pens, n_fits, smem, fits, prog, args, st);
+  return e;
+}
+
+int dense_kt_bucket(int K) { return K == 1 ? 1 : K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32; }
 
 }  // namespace sgd

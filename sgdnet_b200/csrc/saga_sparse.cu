@@ -177,18 +177,6 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
   while (!mbar_test_wait(bar, par)) __nanosleep(SGD_SLEEP_NS);
 }
 
-// gch / n with n an integer below 2^32: q = a*(1/n) corrected once with the exact residual is the correctly rounded
-// quotient (the residual step leaves a relative error of 2^-104 while a/n stays 2^-86 away from every rounding
-// boundary because n has at most 32 significant bits), so this returns the same bits as the IEEE division the
-// reference performs. Operands outside the safe exponent range (and zero, to keep its sign) take the division.
-__device__ __forceinline__ double div_by_n(double a, double nd, double rn) {
-  const double aa = fabs(a);
-  if (__builtin_expect(!(aa > 1e-270 && aa < 1e270), 0)) return a / nd;
-  const double q0 = a * rn;
-  const double r0 = fma(-q0, nd, a);
-  return fma(r0, rn, q0);
-}
-
 // ---- conflict codes: for every row instance q = epoch*n + t of the staged sequence and every nonzero position e of
 // its row, a 16-bit entry about the most recent earlier row OF THE SAME EPOCH within `window` rows that holds the same
 // feature: bits 0-3 its distance d (0 = no such row), bits 4-10 the feature's position in that row (where its

@@ -52,3 +52,24 @@ def test_log_is_faithful(arith):
     assert worst < 1.0
     assert arith.t_log(1.0) == 0.0 and arith.t_log(0.0) == -np.inf and arith.t_log(np.inf) == np.inf
     assert np.isnan(arith.t_log(-1.0))
+
+
+def test_soft_threshold_select_form_equals_the_reference_form():
+    """sgdnet_b200/csrc/common.cuh evaluates SoftThreshold (reference src/prox.h:32-39, std::max semantics) as
+    t = |x| - s; t <= 0 ? +0 : copysign(t, x). Same bits for every finite x and s >= 0, NaN stays NaN."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    x = np.concatenate([rng.normal(size=200000) * 10.0 ** rng.integers(-12, 12, size=200000),
+                        [0.0, 1.0, -1.0, 1e-320, -1e-320, 1e308, -1e308, np.inf, -np.inf, 3.0, -3.0, 2.5, np.nan]])
+    s = np.concatenate([np.abs(rng.normal(size=200000)) * 10.0 ** rng.integers(-12, 12, size=200000),
+                        [0.0, 1.0, 1.0, 0.0, 1e-320, 1e308, 1e308, 1.0, np.inf, 3.0, 3.0, 0.0, 1.0]])
+    # sweep near-ties: x within a few ulps of +-s
+    xt = np.nextafter(s[:1000], np.inf) * np.where(np.arange(1000) % 2 == 0, 1.0, -1.0)
+    x, s = np.concatenate([x, xt, s[:1000], -s[:1000]]), np.concatenate([s, s[:1000], s[:1000], s[:1000]])
+    with np.errstate(invalid="ignore", over="ignore"):
+        a, b = x - s, -x - s
+        ref = np.where(a < 0.0, 0.0, a) - np.where(b < 0.0, 0.0, b)        # std::max(v, 0.0) is (v < 0.0) ? 0.0 : v
+        t = np.abs(x) - s
+        alt = np.where(t <= 0.0, 0.0, np.copysign(t, x))
+    nan = np.isnan(ref)
+    np.testing.assert_array_equal(nan, np.isnan(alt))
+    np.testing.assert_array_equal(ref[~nan].view(np.int64), alt[~nan].view(np.int64))
