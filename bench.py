@@ -125,6 +125,7 @@ def run_reference(args, rank, world):
     from oracle_lib import load_oracle
     from sgdnet_b200 import _abi
     oracle = load_oracle()
+    oracle.lib.oracle_set_arith(0)      # std::exp/std::log, sequential sums: the most literal reading of the reference
     # bounded sample: the same generator at n rows capped so that warmup+steps epochs stay near --cpu-seconds
     est_rate = 0.4e6
     n = int(min(args.n, max(20_000, est_rate * args.cpu_seconds / max(1, args.steps + args.warmup))))
@@ -239,8 +240,16 @@ def main():
     peak, peak_src = peaks()
     per_launch_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
     achieved = n * B_UPD / per_launch_s / 1e9
+    traffic, traffic_src = None, None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
+        with open(os.path.join(ROOT, "profiles", "r1_02_wave_final_ncu_summary.json")) as fh:
+            prof = json.load(fh)
+        if n == prof["updates_per_launch"]:
+            traffic, traffic_src = prof["dram_bytes_per_launch"], "profiles/r1_02_wave_final_ncu_summary.json"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "saga_sparse_wave_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_update": B_UPD, "updates_per_launch": n, "launch_ms": per_launch_s * 1e3,
                 "note": "serial recurrence: one CTA per fit, bounded by the intercept/gradient chain (about 500 cycles per update), not by HBM (DESIGN.md)"}
     lib.sym("session_destroy")(sess)
@@ -273,6 +282,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle_lib import load_oracle
         oracle = load_oracle()
+        oracle.lib.oracle_set_arith(0)  # the reference's own arithmetic (libm, sequential sums), not the pinned one
         n_cpu = int(min(n, max(20_000, 0.4e6 * args.cpu_seconds / 3)))
         xs, ys = make_workload(n_cpu, args.p) if n_cpu != n else (x, y)
         lam = path_lambda(oracle, xs, ys, args.lambda_ind)

@@ -21,15 +21,32 @@ x, y = synth.binomial_sparse(n, p, 50, seed=1005)
 perm = np.random.Generator(np.random.PCG64(1005)).permutation(n)
 foldid = (perm % 10) + 1
 lib = sg.product()
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+shard = None
+if world > 1:      # one process per GPU (torchrun): fold fits dealt to the ranks, one all_gather of the score rows
+    import torch
+    import torch.distributed as dist
+    from sgdnet_b200.shard import Shard
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.check(lib.sym("set_device")(local), "set_device")
+    shard = Shard.from_torch()
+    dist.barrier()
 t0 = time.perf_counter()
 cv = sg.cv_sgdnet(x, y, family="binomial", alpha=[0.0, 0.25, 0.5, 0.75, 1.0], foldid=foldid, nlambda=nlambda,
-                  standardize=False, maxit=maxit, seed=1000, backend=lib)
+                  standardize=False, maxit=maxit, seed=1000, backend=lib, shard=shard)
+if world > 1:
+    dist.barrier()
 wall = time.perf_counter() - t0
+mine = [f for f in cv.fold_fits if f is not None]
 upd_full = sum(int(f.npasses) * n for f in cv.fits)
-upd_fold = sum(int(f.npasses) * f.nobs for f in cv.fold_fits)
+upd_fold = sum(int(f.npasses) * f.nobs for f in mine)
 solver_full = max(f.raw.seconds_solver for f in cv.fits)
-solver_fold = max(f.raw.seconds_solver for f in cv.fold_fits)
-print(json.dumps({"workload": f"cv_sgdnet 10 folds x 5 alphas, binomial sparse {n}x{p}, 50 nnz/row, nlambda={nlambda}, maxit={maxit}",
+solver_fold = max(f.raw.seconds_solver for f in mine)
+if world > 1:
+    dist.destroy_process_group()
+if rank == 0:
+  print(json.dumps({"n_gpus": world, "fold_fits_on_rank0": len(mine),"workload": f"cv_sgdnet 10 folds x 5 alphas, binomial sparse {n}x{p}, 50 nnz/row, nlambda={nlambda}, maxit={maxit}",
                   "fits": len(cv.fits) + len(cv.fold_fits), "wall_s": wall, "fits_per_s": (len(cv.fits) + len(cv.fold_fits)) / wall,
                   "updates_full_fits": upd_full, "updates_fold_fits": upd_fold,
                   "solver_s_full_phase": solver_full, "solver_s_fold_phase": solver_fold,
