@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--p", type=int, default=100_000)
+    ap.add_argument("--rows", dest="n", type=int, default=1_000_000, help="n (rows of X); the metric is quoted at the default")
+    ap.add_argument("--cols", dest="p", type=int, default=100_000, help="p (columns of X)")
     ap.add_argument("--lambda-ind", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the bounded oracle sample")
     ap.add_argument("--e2e-epochs", type=int, default=16, help="epochs of the bounded sgdnet_fit_sparse call of the e2e leg")
