@@ -184,57 +184,108 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 // ran serially). Lane l of a worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
 constexpr uint32_t kCodeGlobal = 1u << 11;
 
+constexpr int kDepRows = 32;      // row instances per block iteration (4 per warp)
+constexpr int kDepMaxWindow = 15;  // distances are 4-bit
+constexpr int kDepBitWords = 64;
+__device__ __forceinline__ uint32_t dep_hash(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 21; }   // 11 bits
+
 __global__ void __launch_bounds__(256)
 wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
                  int window) {
+  // the index runs of the block's rows and of the `window` rows before them, staged once in shared memory: the
+  // membership searches below then never leave the SM
+  __shared__ int32_t sidx[kDepRows + kDepMaxWindow][kCap];
+  __shared__ uint32_t sbits[kDepRows + kDepMaxWindow][kDepBitWords];   // hashed 2048-bit membership filter per row
+  __shared__ int32_t snnz[kDepRows + kDepMaxWindow];
+  __shared__ uint32_t ssamp[kDepRows + kDepMaxWindow];
   const int fit_id = blockIdx.y;
   const RoundArgs ra = args[fit_id];
   if (ra.n_epochs <= 0 || prog[fit_id].status != kRunning || ra.dep == nullptr) return;
   const FitDev& f = fits[fit_id];
   const int64_t n = f.n;
   const int64_t total = n * ra.n_epochs;
-  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int64_t warp_global = int64_t(blockIdx.x) * nwarps + (threadIdx.x >> 5);
-  const int64_t warp_stride = int64_t(gridDim.x) * nwarps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int32_t* __restrict__ ci = f.ci;
-  for (int64_t q = warp_global; q < total; q += warp_stride) {
-    const int64_t t = q % n;
-    const uint32_t* __restrict__ eseq = ra.seq + (q - t);
-    const uint32_t s = eseq[t];
-    const RowInfo ri = f.rows[s];
-    int j[kChunks];
-    uint32_t ent[kChunks];
+  const int nslots = kDepRows + window;
+  const int64_t n_chunks = (total + kDepRows - 1) / kDepRows;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t q0 = chunk * kDepRows;
+    __syncthreads();                                   // the previous iteration's searches are done
+    for (int r = warp; r < nslots; r += nwarps) {      // slot r holds row instance q0 - window + r
+      const int64_t q = q0 - window + r;
+      int32_t nnz = 0;
+      uint32_t s = 0xffffffffu;
+      sbits[r][lane] = 0u;
+      sbits[r][lane + 32] = 0u;
+      __syncwarp();
+      if (q >= 0 && q < total) {
+        s = ra.seq[q];
+        const RowInfo ri = f.rows[s];
+        nnz = ri.nnz;
+        if (nnz <= kCap) {
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      const int e = c * 32 + lane;
-      j[c] = (ri.nnz <= kCap && e < ri.nnz) ? ci[ri.start + e] : -1;
-      ent[c] = 0;
-    }
-    uint32_t dupd = 0;
-    const int dmax = static_cast<int>(t < window ? t : window);
-    for (int d = 1; d <= dmax; ++d) {
-      const uint32_t s2 = eseq[t - d];
-      if (s2 == s && dupd == 0) dupd = static_cast<uint32_t>(d);
-      const RowInfo r2 = f.rows[s2];
-      if (r2.nnz == 0) continue;
-      const int32_t* __restrict__ c2 = ci + r2.start;
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        if (j[c] < 0 || ent[c] != 0) continue;
-        if (r2.nnz > kCap) {
-          ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
-          continue;
+          for (int c = 0; c < kChunks; ++c) {
+            const int e = c * 32 + lane;
+            if (e < nnz) {
+              const int32_t jj = ci[ri.start + e];
+              sidx[r][e] = jj;
+              const uint32_t h = dep_hash(jj);
+              atomicOr(&sbits[r][h >> 5], 1u << (h & 31u));
+            }
+          }
         }
-        int lo = 0, hi = r2.nnz;             // first position with c2[pos] >= j[c]
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
-        }
-        if (lo < r2.nnz && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
+      }
+      if (lane == 0) {
+        snnz[r] = nnz;
+        ssamp[r] = s;
       }
     }
-    ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
-    if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd);
+    __syncthreads();
+    for (int rl = warp; rl < kDepRows; rl += nwarps) {
+      const int64_t q = q0 + rl;
+      if (q >= total) break;
+      const int64_t t = q % n;
+      const int me = window + rl;
+      const int32_t nnz = snnz[me];
+      const uint32_t s = ssamp[me];
+      int j[kChunks];
+      uint32_t ent[kChunks], hw[kChunks], hb[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int e = c * 32 + lane;
+        j[c] = (nnz <= kCap && e < nnz) ? sidx[me][e] : -1;
+        ent[c] = 0;
+        const uint32_t h = dep_hash(j[c]);
+        hw[c] = h >> 5;
+        hb[c] = 1u << (h & 31u);
+      }
+      uint32_t dupd = 0;
+      const int dmax = static_cast<int>(t < window ? t : window);
+      for (int d = 1; d <= dmax; ++d) {
+        const int pr = me - d;
+        if (ssamp[pr] == s && dupd == 0) dupd = static_cast<uint32_t>(d);
+        const int32_t nnz2 = snnz[pr];
+        if (nnz2 == 0) continue;
+        const int32_t* __restrict__ c2 = sidx[pr];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          if (j[c] < 0 || ent[c] != 0) continue;
+          if (nnz2 > kCap) {
+            ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
+            continue;
+          }
+          if ((sbits[pr][hw[c]] & hb[c]) == 0u) continue;   // certainly absent (no false negatives)
+          int lo = 0, hi = nnz2;               // first position with c2[pos] >= j[c]
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
+          }
+          if (lo < nnz2 && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
+        }
+      }
+      ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
+      if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd);
+    }
   }
 }
 
@@ -1089,7 +1140,7 @@ static cudaError_t launch_wave(int n_fits, FitDev* fits, Progress* prog, const R
 
 cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* prog, const RoundArgs* args,
                              int64_t max_rows, int sms, cudaStream_t st) {
-  const int64_t want = (max_rows + 7) / 8;
+  const int64_t want = (max_rows + kDepRows - 1) / kDepRows;
   const int64_t cap = std::max<int64_t>(1, int64_t(sms) * 8 / std::max(1, n_fits));
   dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min(want, cap))), n_fits);
   wave_deps_kernel<<<grid, 256, 0, st>>>(fits, prog, args, wave_warps() - 1);
