@@ -45,6 +45,18 @@ double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// SGDNET_TIMING=1: host setup phases to stderr (development aid)
+struct PhaseTimer {
+  bool on = std::getenv("SGDNET_TIMING") != nullptr;
+  double t = now_s();
+  void lap(const char* what) {
+    if (!on) return;
+    const double u = now_s();
+    std::fprintf(stderr, "[sgdnet_b200] %-28s %8.1f ms\n", what, (u - t) * 1e3);
+    t = u;
+  }
+};
+
 // Device memory owned by one engine; freed together.
 struct Arena {
   std::vector<void*> ptrs;
@@ -62,6 +74,12 @@ struct Arena {
   T* upload(const std::vector<T>& v) {
     T* p = alloc<T>(v.size(), false);
     if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+  }
+  template <typename T>
+  T* upload_from(const T* src, size_t count) {
+    T* p = alloc<T>(count, false);
+    if (count) CK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
     return p;
   }
   template <typename T>
@@ -162,15 +180,18 @@ struct Engine {
     auto it = designs.find(key);
     if (it != designs.end()) return it->second;
     auto hd = std::make_shared<HostDesign>();
+    PhaseTimer pt;
     hd->build(raw, rows, n_rows, standardize);
+    pt.lap("design build (host)");
     DeviceDesign dd;
     if (hd->sparse) {
-      dd.rows = arena.upload(hd->rows);
-      dd.ci = arena.upload(hd->ci);
-      dd.cv = arena.upload(hd->cv);
+      dd.rows = arena.upload_from(hd->rows_v, static_cast<size_t>(hd->n));
+      dd.ci = arena.upload_from(hd->ci_v, hd->n_entries);
+      dd.cv = arena.upload_from(hd->cv_v, hd->n_entries);
     } else {
       dd.xd = arena.upload(hd->xd);
     }
+    pt.lap("design upload");
     dd.c = arena.upload(hd->c);
     dd.x_center = arena.upload(hd->x_center);
     dd.x_scale = arena.upload(hd->x_scale);
@@ -196,8 +217,10 @@ struct Engine {
     for (int k = 0; k < Ky; ++k)
       for (int64_t i = 0; i < d.n; ++i)
         ysub[static_cast<size_t>(k) * d.n + i] = y_cm[static_cast<size_t>(k) * raw.n + (rows ? rows[i] : i)];
+    PhaseTimer pt;
     std::string err = job.plan.build(d, std::move(ysub), Ky, ctl);
     if (!err.empty()) return err;
+    pt.lap("plan (lambda path, steps)");
     job.rng = rng;
     job.test_rows = test_rows;
     job.n_test = n_test;
@@ -264,6 +287,7 @@ struct Engine {
       job.dup_dev = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
     }
     jobs.push_back(std::move(job));
+    pt.lap("state alloc + upload");
     return "";
   }
 
@@ -591,8 +615,10 @@ struct XArg {
 };
 
 void load_x(Engine& eng, const XArg& xa, const double* y, int32_t y_cols) {
+  PhaseTimer pt;
   if (xa.sparse) eng.raw.from_csc(xa.ci, xa.cp, xa.cx, xa.n, xa.p);
   else eng.raw.from_dense(xa.x, xa.n, xa.p);
+  pt.lap("CSC -> CSR");
   eng.Ky = y_cols;
   if (y) eng.y_cm.assign(y, y + static_cast<size_t>(xa.n) * y_cols);
 }
@@ -816,9 +842,7 @@ static int session_create(const XArg& xa, const double* y, int32_t y_cols, const
     std::string err = s->eng.add_fit(nullptr, xa.n, *control, &placeholder, nullptr, 0);
     if (!err.empty()) return fail(SGDNET_ERR_ARG, err);
     s->eng.finalize_batch();
-    s->eng.raw.rp.clear(); s->eng.raw.rp.shrink_to_fit();
-    s->eng.raw.ci.clear(); s->eng.raw.ci.shrink_to_fit();
-    s->eng.raw.cv.clear(); s->eng.raw.cv.shrink_to_fit();
+    s->eng.raw.release_rows();
     *out = s.release();
     return SGDNET_OK;
   });
