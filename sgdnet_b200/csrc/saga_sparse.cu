@@ -186,18 +186,21 @@ constexpr uint32_t kCodeGlobal = 1u << 11;
 
 constexpr int kDepRows = 32;      // row instances per block iteration (4 per warp)
 constexpr int kDepMaxWindow = 15;  // distances are 4-bit
-constexpr int kDepBitWords = 64;
-__device__ __forceinline__ uint32_t dep_hash(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 21; }   // 11 bits
+constexpr int kDepBitWords = 256;  // 8192-bit filter per row, two hash functions: ~0.06 % false positives at 100 entries
+__device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 19; }   // 13 bits
+__device__ __forceinline__ uint32_t dep_hash2(int32_t j) { return (static_cast<uint32_t>(j) * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
 
 __global__ void __launch_bounds__(256)
 wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
                  int window) {
   // the index runs of the block's rows and of the `window` rows before them, staged once in shared memory: the
   // membership searches below then never leave the SM
-  __shared__ int32_t sidx[kDepRows + kDepMaxWindow][kCap];
-  __shared__ uint32_t sbits[kDepRows + kDepMaxWindow][kDepBitWords];   // hashed 2048-bit membership filter per row
-  __shared__ int32_t snnz[kDepRows + kDepMaxWindow];
-  __shared__ uint32_t ssamp[kDepRows + kDepMaxWindow];
+  extern __shared__ __align__(16) unsigned char deps_smem[];
+  const int nslots_alloc = kDepRows + window;
+  int32_t (*sidx)[kCap] = reinterpret_cast<int32_t (*)[kCap]>(deps_smem);
+  uint32_t (*sbits)[kDepBitWords] = reinterpret_cast<uint32_t (*)[kDepBitWords]>(deps_smem + size_t(nslots_alloc) * kCap * 4);   // hashed membership filter per row
+  int32_t* snnz = reinterpret_cast<int32_t*>(deps_smem + size_t(nslots_alloc) * (kCap + kDepBitWords) * 4);
+  uint32_t* ssamp = reinterpret_cast<uint32_t*>(snnz + nslots_alloc);
   const int fit_id = blockIdx.y;
   const RoundArgs ra = args[fit_id];
   if (ra.n_epochs <= 0 || prog[fit_id].status != kRunning || ra.dep == nullptr) return;
@@ -215,8 +218,8 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
       const int64_t q = q0 - window + r;
       int32_t nnz = 0;
       uint32_t s = 0xffffffffu;
-      sbits[r][lane] = 0u;
-      sbits[r][lane + 32] = 0u;
+#pragma unroll
+      for (int wd = 0; wd < kDepBitWords / 32; ++wd) sbits[r][lane + 32 * wd] = 0u;
       __syncwarp();
       if (q >= 0 && q < total) {
         s = ra.seq[q];
@@ -229,8 +232,9 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
             if (e < nnz) {
               const int32_t jj = ci[ri.start + e];
               sidx[r][e] = jj;
-              const uint32_t h = dep_hash(jj);
-              atomicOr(&sbits[r][h >> 5], 1u << (h & 31u));
+              const uint32_t h1 = dep_hash1(jj), h2 = dep_hash2(jj);
+              atomicOr(&sbits[r][h1 >> 5], 1u << (h1 & 31u));
+              atomicOr(&sbits[r][h2 >> 5], 1u << (h2 & 31u));
             }
           }
         }
@@ -249,15 +253,17 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
       const int32_t nnz = snnz[me];
       const uint32_t s = ssamp[me];
       int j[kChunks];
-      uint32_t ent[kChunks], hw[kChunks], hb[kChunks];
+      uint32_t ent[kChunks], hw[kChunks], hb[kChunks], hw2[kChunks], hb2[kChunks];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int e = c * 32 + lane;
         j[c] = (nnz <= kCap && e < nnz) ? sidx[me][e] : -1;
         ent[c] = 0;
-        const uint32_t h = dep_hash(j[c]);
-        hw[c] = h >> 5;
-        hb[c] = 1u << (h & 31u);
+        const uint32_t h1 = dep_hash1(j[c]), h2 = dep_hash2(j[c]);
+        hw[c] = h1 >> 5;
+        hb[c] = 1u << (h1 & 31u);
+        hw2[c] = h2 >> 5;
+        hb2[c] = 1u << (h2 & 31u);
       }
       uint32_t dupd = 0;
       const int dmax = static_cast<int>(t < window ? t : window);
@@ -274,7 +280,7 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
             ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
             continue;
           }
-          if ((sbits[pr][hw[c]] & hb[c]) == 0u) continue;   // certainly absent (no false negatives)
+          if ((sbits[pr][hw[c]] & hb[c]) == 0u || (sbits[pr][hw2[c]] & hb2[c]) == 0u) continue;   // certainly absent
           int lo = 0, hi = nnz2;               // first position with c2[pos] >= j[c]
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -1143,7 +1149,15 @@ cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* pro
   const int64_t want = (max_rows + kDepRows - 1) / kDepRows;
   const int64_t cap = std::max<int64_t>(1, int64_t(sms) * 8 / std::max(1, n_fits));
   dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min(want, cap))), n_fits);
-  wave_deps_kernel<<<grid, 256, 0, st>>>(fits, prog, args, wave_warps() - 1);
+  const int window = wave_warps() - 1;
+  const size_t smem = size_t(kDepRows + window) * ((kCap + kDepBitWords) * 4 + 8);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  wave_deps_kernel<<<grid, 256, smem, st>>>(fits, prog, args, window);
   return cudaGetLastError();
 }
 
