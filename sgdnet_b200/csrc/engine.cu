@@ -57,16 +57,40 @@ struct PhaseTimer {
   }
 };
 
-// Device memory owned by one engine; freed together.
+// Device and pinned host memory owned by one engine; freed together. Sub-allocated from a few large slabs: a batch of
+// cv fits makes thousands of small allocations, and thousands of cudaMalloc / cudaFree / cudaMallocHost calls cost
+// seconds (cudaFree synchronises the device every time).
 struct Arena {
-  std::vector<void*> ptrs;
-  std::vector<void*> pinned;
+  struct Slab {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+  };
+  std::vector<Slab> dev, pin;
+  static constexpr size_t kAlign = 256;
+  static constexpr size_t kDevSlab = size_t(128) << 20, kPinSlab = size_t(8) << 20;
+
+  void* carve(std::vector<Slab>& slabs, size_t bytes, size_t slab_size, bool pinned) {
+    bytes = (std::max<size_t>(bytes, 1) + kAlign - 1) & ~(kAlign - 1);
+    for (Slab& s : slabs)
+      if (s.size - s.used >= bytes) {
+        void* p = s.base + s.used;
+        s.used += bytes;
+        return p;
+      }
+    Slab s;
+    s.size = std::max(bytes, slab_size);
+    void* p = nullptr;
+    if (pinned) CK(cudaMallocHost(&p, s.size));
+    else CK(cudaMalloc(&p, s.size));
+    s.base = static_cast<char*>(p);
+    s.used = bytes;
+    slabs.push_back(s);
+    return p;
+  }
   template <typename T>
   T* alloc(size_t count, bool zero = true) {
-    void* p = nullptr;
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CK(cudaMalloc(&p, bytes));
-    ptrs.push_back(p);
+    void* p = carve(dev, bytes, kDevSlab, false);
     if (zero) CK(cudaMemset(p, 0, bytes));
     return static_cast<T*>(p);
   }
@@ -84,14 +108,11 @@ struct Arena {
   }
   template <typename T>
   T* host(size_t count) {
-    void* p = nullptr;
-    CK(cudaMallocHost(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    pinned.push_back(p);
-    return static_cast<T*>(p);
+    return static_cast<T*>(carve(pin, std::max<size_t>(count, 1) * sizeof(T), kPinSlab, true));
   }
   ~Arena() {
-    for (void* p : ptrs) cudaFree(p);
-    for (void* p : pinned) cudaFreeHost(p);
+    for (Slab& s : dev) cudaFree(s.base);
+    for (Slab& s : pin) cudaFreeHost(s.base);
   }
 };
 
