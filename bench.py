@@ -11,12 +11,13 @@ libsgdnet_b200.so.
                setup, a bounded stretch of the lambda path, archives back to the host, all inside the timed region
   roofline     HBM roofline of the dominant kernel (saga_sparse_wave_kernel): algorithmic bytes per update
                (12*nnz_row + 8 + 4 + 8*K_y + 16*K = 1236 B) x updates per launch / kernel time
-  cpu_baseline the CPU oracle (restated reference algorithm, g++ -O2, 1 thread: the reference is single-threaded) on
-               a bounded sample of the same workload, timed on this box
+  cpu_baseline the reference's CPU path (oracle/_ref, else the restated oracle; g++ -O2, 1 thread: the reference is
+               single-threaded) on a bounded sample of the same workload, timed on this box
 
 One process per GPU. A single fit does not shard (the solver is a serial recurrence); with --gpus N every rank runs an
 independent fit of the same shape (what cv folds / alpha grids are), no data-path collective: scaling = weak.
-`--impl reference` times the CPU oracle arm instead (the reference itself needs R + Rcpp + Eigen: not buildable here).
+`--impl reference` times the CPU arm instead: oracle/_ref (the reference's own solver sources compiled against a stand-in
+for Rcpp/Eigen, which are not in the image) when it was built, else the restated oracle.
 """
 import argparse
 import ctypes as C
@@ -118,14 +119,27 @@ def control_for(lib, n_lambda=100, lambda_=None, maxit=1000):
                              debug=False)
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle, single thread, `steps` epochs at the same lambda of the same workload."""
-    if rank != 0:
-        return
-    from oracle_lib import load_oracle
-    from sgdnet_b200 import _abi
+def cpu_arm():
+    """The CPU implementation that is timed: oracle/_ref (the reference's own src/sgdnet.cpp compiled against the
+    Rcpp/Eigen stand-in, kind "reference") when it was built, else the restated oracle in its libm arithmetic (kind
+    "port"). The two produce identical bits (tests/test_ref_cpu.py)."""
+    from oracle_lib import load_oracle, load_reference_build
+    ref = load_reference_build()
+    if ref is not None:
+        ref.lib.ref_set_force_debug(0)      # per-epoch loss passes are only needed for the tests' epoch counts
+        return ref, "reference", ("reference src/sgdnet.cpp + saga-sparse.h compiled unmodified (g++ -O2, no FMA contraction) against "
+                                  "the Rcpp/Eigen stand-in of oracle/refbuild (no R/Eigen in the image), 1 thread: the reference is single-threaded")
     oracle = load_oracle()
     oracle.lib.oracle_set_arith(0)      # std::exp/std::log, sequential sums: the most literal reading of the reference
+    return oracle, "port", "CPU oracle restatement (libm arithmetic), g++ -O2, 1 thread: the reference is single-threaded"
+
+
+def run_reference(args, rank, world):
+    """CPU arm, single thread, `steps` epochs at the same lambda of the same workload."""
+    if rank != 0:
+        return
+    from sgdnet_b200 import _abi
+    oracle, kind, kind_note = cpu_arm()
     # bounded sample: the same generator at n rows capped so that warmup+steps epochs stay near --cpu-seconds
     est_rate = 0.4e6
     n = int(min(args.n, max(20_000, est_rate * args.cpu_seconds / max(1, args.steps + args.warmup))))
@@ -152,9 +166,9 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, n_used=n),
-        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": 1, "kind": kind,
                          "sample": f"last {args.steps} of {raw.npasses} epochs of n={n} rows (same generator, p={args.p}, {NNZ_ROW} nnz/row) at lambda[{args.lambda_ind}]; "
-                                   "reference needs R+Rcpp+Eigen and cannot be built here: CPU oracle restatement (libm arithmetic), g++ -O2, 1 thread"},
+                                   + kind_note},
         "e2e": {"value": n * raw.npasses / wall, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -288,9 +302,7 @@ def main():
     # ---------------- cpu baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle_lib import load_oracle
-        oracle = load_oracle()
-        oracle.lib.oracle_set_arith(0)  # the reference's own arithmetic (libm, sequential sums), not the pinned one
+        oracle, cpu_kind, cpu_note = cpu_arm()
         n_cpu = int(min(n, max(20_000, 0.4e6 * args.cpu_seconds / 3)))
         xs, ys = make_workload(n_cpu, args.p) if n_cpu != n else (x, y)
         lam = path_lambda(oracle, xs, ys, args.lambda_ind)
@@ -300,9 +312,9 @@ def main():
             return oracle.fit(xs, ys.reshape(-1, 1), ctl3, oracle.rng_from_seed(1))
         rawc, raww = run_cpu(3), run_cpu(1)             # epochs 2-3 are timed (epoch 1 runs on a cold cache)
         cpu_s = rawc.seconds_solver - raww.seconds_solver
-        cpu = {"value": n_cpu * 2 / cpu_s, "unit": "updates/s", "cores": 1, "kind": "port",
+        cpu = {"value": n_cpu * 2 / cpu_s, "unit": "updates/s", "cores": 1, "kind": cpu_kind,
                "sample": f"epochs 2-3 of a 3-epoch fit of n={n_cpu} rows (same generator, p={args.p}, {NNZ_ROW} nnz/row) at lambda[{args.lambda_ind}]; "
-                         "solver loop only; reference is single-threaded; real R/Rcpp build not available (no R/Eigen in image)",
+                         + cpu_note,
                "host_cores_available": os.cpu_count()}
 
     if rank == 0:

@@ -15,13 +15,17 @@
  *   sampling          R core RNG (MT19937 + set.seed scrambling + unif_rand fixup), call sites
  *                     src/saga-dense.h:152, src/saga-sparse.h:261
  *
- * PARITY STATUS.  The reference cannot be compiled here (needs R, Rcpp, RcppEigen/Eigen; none is in
- * the image, no network) and its test-suite holds no golden vectors (it compares with glmnet/lm/glm
- * at 1e-3..1e-6).  This oracle is pinned by (i) the R RNG known-answer values, (ii) the reference
- * tests' own properties re-expressed in tests/test_oracle_*.py (closed forms, lambda_max formulas,
- * null deviances, sparse==dense, ...).  Bit-level agreement with a real R build is UNPINNED: Eigen's
- * dense GEMV/.sum() reduction order is implementation-defined; here every reduction is a plain
- * ascending-index sequential sum.
+ * PARITY STATUS.  PINNED AGAINST THE REFERENCE'S OWN CODE.  R, Rcpp and Eigen are not in the image, so the reference's
+ * package cannot be built; but its solver sources compile unmodified, from where they lie, against a minimal stand-in
+ * for the Rcpp/Eigen subset they use (oracle/refbuild/: recipe, stand-in header, C entry points -> oracle/_ref/
+ * libsgdnet_ref.so).  In "libm" mode this oracle reproduces that build BIT FOR BIT - lambda path, epochs per lambda,
+ * return codes, coefficients, intercepts, deviance ratios, null deviance, debug losses - on the bundled datasets and on
+ * a grid of families x penalties x {dense, sparse} x intercept x standardize (tests/test_ref_cpu.py, live against the
+ * library and against the committed outputs tests/golden/ref_vectors.npz).  Also pinned by (i) the R RNG known-answer
+ * values, (ii) the reference tests' own properties re-expressed in tests/test_oracle_cpu.py (closed forms, lambda_max
+ * formulas, null deviances, sparse==dense, ...).  What stays unpinned is the part of a real R build that Eigen leaves
+ * implementation-defined: the association of dense reductions (GEMV, .sum(), .norm()) and packet exp/log; the stand-in
+ * and this oracle's libm mode use plain ascending sequential sums and std::exp/std::log.
  *
  * ARITHMETIC MODES (oracle_set_arith / env SGDNET_ORACLE_ARITH):
  *   1 "portable" (default): inside the solver loop, exp/log are sgd_exp/sgd_log and the dot products / class sums use

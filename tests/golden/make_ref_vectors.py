@@ -1,0 +1,109 @@
+"""Golden OUTPUT vectors from the reference's own code, compiled and run in the build container.
+
+oracle/_ref/libsgdnet_ref.so is /root/reference/src/sgdnet.cpp (+ the headers it includes), unmodified, compiled against
+the Rcpp/Eigen stand-in of oracle/refbuild/ (recipe: oracle/refbuild/Makefile). This script runs it through the same
+Python mirror of R/sgdnet.R that the tests use (sgdnet_b200/api.py) on the reference's bundled datasets and on small
+seeded synthetic inputs, and stores inputs + outputs in tests/golden/ref_vectors.npz, which travels to the GPU box
+(where neither /root/reference nor a compiler run of it exists).
+
+Run once in the build container:  make -C oracle/refbuild && python tests/golden/make_ref_vectors.py
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import sgdnet_b200 as sg
+from sgdnet_b200 import synth
+from sgdnet_b200._abi import Library
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libsgdnet_ref.so")
+
+
+def inputs():
+    """input key -> (x, y): the reference's bundled datasets (tests/golden/*.npz) and small seeded synthetic designs."""
+    g = lambda n: np.load(os.path.join(HERE, n + ".npz"))
+    ab, he, wi, st = g("abalone"), g("heart"), g("wine"), g("student")
+    return {
+        "abalone": (ab["x"], ab["y"]),
+        "heart": (sp.csc_matrix((he["x_x"], he["x_i"], he["x_p"]), shape=tuple(he["x_shape"])), he["y"]),
+        "wine": (wi["x"], wi["y"]),
+        "student": (st["x"], st["y"]),
+        # BASELINE config 2 / 5 shape in miniature (sparse binomial, 16 nnz/row)
+        "c2mini": synth.binomial_sparse(1500, 300, 16, seed=1002),
+        "sparse_gaussian": synth.random_data(200, 8, "gaussian", True, density=0.3, seed=5),
+        "c3mini": synth.multinomial_dense(400, 30, 4, seed=1003),
+        "c4mini": synth.mgaussian_dense(300, 40, 3, seed=1004),
+        "sparse_multinomial": synth.random_data(150, 6, "multinomial", True, density=0.5, seed=8),
+    }
+
+
+BUNDLED = ("abalone", "heart", "wine", "student")   # already fixtures of their own; not stored twice
+
+CASES = {
+    # BASELINE config 1 exactly (R defaults: standardize, intercept, thresh 1e-3, maxit 1000, set.seed(1))
+    "c1_abalone_gaussian_enet": ("abalone", dict(family="gaussian", alpha=0.5, seed=1)),
+    "heart_binomial_lasso_sparse": ("heart", dict(family="binomial", alpha=1.0, standardize=False, nlambda=20, seed=1)),
+    "heart_binomial_enet_sparse_std": ("heart", dict(family="binomial", alpha=0.5, standardize=True, nlambda=10, seed=2)),
+    "wine_multinomial_enet": ("wine", dict(family="multinomial", alpha=0.8, nlambda=15, seed=1)),
+    "student_mgaussian_grouplasso": ("student", dict(family="mgaussian", alpha=1.0, nlambda=15, seed=1)),
+    "student_mgaussian_ridge_stdresp": ("student", dict(family="mgaussian", alpha=0.0, nlambda=8, standardize_response=True, seed=3)),
+    "c2mini_sparse_binomial_lasso": ("c2mini", dict(family="binomial", alpha=1.0, standardize=False, nlambda=12, maxit=200, seed=1)),
+    "c2mini_sparse_binomial_enet": ("c2mini", dict(family="binomial", alpha=0.5, standardize=False, nlambda=12, maxit=200, seed=1)),
+    "c2mini_sparse_binomial_ridge": ("c2mini", dict(family="binomial", alpha=0.0, standardize=False, nlambda=12, maxit=200, seed=1)),
+    "c2mini_sparse_binomial_nointercept": ("c2mini", dict(family="binomial", alpha=1.0, standardize=False, intercept=False,
+                                                          nlambda=8, maxit=200, seed=4)),
+    "sparse_gaussian_ridge_wscale": ("sparse_gaussian", dict(family="gaussian", alpha=0.0, standardize=False, nlambda=6, seed=6)),
+    "c3mini_dense_multinomial": ("c3mini", dict(family="multinomial", alpha=0.8, nlambda=10, maxit=200, seed=1)),
+    "c4mini_dense_mgaussian": ("c4mini", dict(family="mgaussian", alpha=1.0, nlambda=10, maxit=200, seed=1)),
+    "sparse_multinomial_std": ("sparse_multinomial", dict(family="multinomial", alpha=0.5, standardize=True, nlambda=6, maxit=100, seed=9)),
+    # fixed path lengths (thresh = 0: every lambda runs exactly maxit epochs unless all coefficients are exactly zero),
+    # so that arithmetic with another summation order can be held to the 1e-6 tolerance on identical sampling sequences
+    "fixed_abalone_gaussian_enet": ("abalone", dict(family="gaussian", alpha=0.5, nlambda=12, thresh=0.0, maxit=4, seed=1)),
+    "fixed_heart_binomial_lasso_sparse": ("heart", dict(family="binomial", alpha=1.0, standardize=False, nlambda=10, thresh=0.0, maxit=6, seed=1)),
+    "fixed_wine_multinomial_enet": ("wine", dict(family="multinomial", alpha=0.8, nlambda=10, thresh=0.0, maxit=6, seed=1)),
+    "fixed_student_mgaussian_grouplasso": ("student", dict(family="mgaussian", alpha=1.0, nlambda=10, thresh=0.0, maxit=6, seed=1)),
+    "fixed_c2mini_sparse_binomial_lasso": ("c2mini", dict(family="binomial", alpha=1.0, standardize=False, nlambda=10, thresh=0.0, maxit=5, seed=1)),
+    "fixed_c2mini_sparse_binomial_enet": ("c2mini", dict(family="binomial", alpha=0.5, standardize=False, nlambda=10, thresh=0.0, maxit=5, seed=1)),
+    "fixed_c2mini_sparse_binomial_ridge": ("c2mini", dict(family="binomial", alpha=0.0, standardize=False, nlambda=10, thresh=0.0, maxit=5, seed=1)),
+    "fixed_c3mini_dense_multinomial": ("c3mini", dict(family="multinomial", alpha=0.8, nlambda=8, thresh=0.0, maxit=5, seed=1)),
+    "fixed_c4mini_dense_mgaussian": ("c4mini", dict(family="mgaussian", alpha=1.0, nlambda=8, thresh=0.0, maxit=5, seed=1)),
+    "fixed_sparse_multinomial_std": ("sparse_multinomial", dict(family="multinomial", alpha=0.5, standardize=True, nlambda=6, thresh=0.0, maxit=5, seed=9)),
+    "fixed_sparse_gaussian_std_nointercept": ("sparse_gaussian", dict(family="gaussian", alpha=0.3, standardize=True, intercept=False, nlambda=6, thresh=0.0, maxit=5, seed=2)),
+}
+
+
+def main():
+    ref = Library(REF_SO, "ref_")
+    store = {}
+    ins = inputs()
+    for key, (x, y) in ins.items():
+        if key in BUNDLED:
+            continue
+        if sp.issparse(x):
+            x = sp.csc_matrix(x)
+            x.sort_indices()
+            store[f"in/{key}/x_i"], store[f"in/{key}/x_p"], store[f"in/{key}/x_x"] = x.indices.astype(np.int32), x.indptr.astype(np.int32), x.data
+            store[f"in/{key}/x_shape"] = np.array(x.shape, dtype=np.int64)
+        else:
+            store[f"in/{key}/x"] = np.asarray(x, dtype=np.float64)
+        store[f"in/{key}/y"] = np.asarray(y)
+    for name, (key, kw) in CASES.items():
+        x, y = ins[key]
+        fit = sg.sgdnet(x, y, backend=ref, **kw).raw
+        for f in ("a0", "beta", "lambda_", "dev_ratio", "return_codes", "epochs"):
+            store[f"out/{name}/{f}"] = getattr(fit, f)
+        store[f"out/{name}/nulldev"] = np.array(fit.nulldev)
+        store[f"out/{name}/npasses"] = np.array(fit.npasses)
+        print(f"{name}: n_lambda={len(fit.lambda_)} npasses={fit.npasses} nnz(beta)={int((fit.beta != 0).sum())}")
+    np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **store)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,3 +21,19 @@ def build_oracle(force=False):
 def load_oracle():
     from sgdnet_b200._abi import Library
     return Library(build_oracle(), "oracle_")
+
+
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsgdnet_ref.so")
+REF_SRC = "/root/reference/src/sgdnet.cpp"
+
+
+def load_reference_build():
+    """oracle/_ref/libsgdnet_ref.so: the reference's own src/sgdnet.cpp (+ headers) compiled from where it lies against
+    the Rcpp/Eigen stand-in of oracle/refbuild/. Built where /root/reference exists; elsewhere the prebuilt file is used.
+    Returns None when neither is available."""
+    if os.path.exists(REF_SRC):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ORACLE_DIR, "refbuild")])
+    if not os.path.exists(REF_SO):
+        return None
+    from sgdnet_b200._abi import Library
+    return Library(REF_SO, "ref_")

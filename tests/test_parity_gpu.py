@@ -165,3 +165,19 @@ def test_cv_batch_matches_sequential_oracle(cuda, oracle):
     for cg, cr in zip(g.cv_raw, r.cv_raw):
         rel_close(cg, cr, what="cv_raw")
     assert g.alpha_min == r.alpha_min and g.lambda_min == r.lambda_min and g.lambda_1se == r.lambda_1se
+
+
+# ---------------------------------------------------------------- against the reference's own compiled code
+from ref_vectors import CASES as REF_CASES, assert_matches_reference, case as ref_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(REF_CASES))
+def test_cuda_matches_reference_build_vectors(cuda, name):
+    """tests/golden/ref_vectors.npz holds the outputs of /root/reference/src/sgdnet.cpp itself (compiled against the
+    Rcpp/Eigen stand-in, oracle/refbuild/). Lambda path exact; the fixed-length cases must agree over the whole path
+    (supports exact, coefficients / intercepts / deviances within 1e-6 relative); converging cases up to the first
+    lambda whose epoch count the summation order moves (tests/ref_vectors.py)."""
+    x, y, kw, exp = ref_case(name)
+    n_cmp = assert_matches_reference(sg.sgdnet(x, y, backend=cuda, **kw).raw, exp, exact=False)
+    if name.startswith("fixed_"):
+        assert n_cmp == len(exp["lambda_"])
