@@ -79,8 +79,14 @@ double R::unif_rand_hook() {
   return refentry::unif(refentry::g_rng);
 }
 
-/* ------------------------------------------------------------------ the reference, unmodified */
+/* ------------------------------------------------------------------ the reference, unmodified
+   (-I$(REF_SRC) resolves this to /root/reference/src/sgdnet.cpp; the shim test build puts -I../../shim first, so the
+   same entry points then wrap shim/sgdnet.cpp, the drop-in replacement that calls libsgdnet_b200.so) */
 #include "sgdnet.cpp"
+
+#ifndef REF_SYM
+#define REF_SYM(name) ref_##name
+#endif
 
 /* ------------------------------------------------------------------ C ABI */
 namespace refentry {
@@ -175,9 +181,9 @@ int guarded(sgdnet_rng* rng, int64_t n, F f) {
 
 extern "C" {
 
-void ref_set_force_debug(int on) { refentry::g_force_debug = on; }
+void REF_SYM(set_force_debug)(int on) { refentry::g_force_debug = on; }
 
-void ref_rng_set_seed(sgdnet_rng* rng, uint32_t seed) {
+void REF_SYM(rng_set_seed)(sgdnet_rng* rng, uint32_t seed) {
   std::memset(rng, 0, sizeof(*rng));
   rng->kind = SGDNET_RNG_MT;
   for (int j = 0; j < 50; ++j) seed = 69069u * seed + 1u;
@@ -190,11 +196,11 @@ void ref_rng_set_seed(sgdnet_rng* rng, uint32_t seed) {
   rng->mti = 624;
 }
 
-double ref_rng_unif(sgdnet_rng* rng) { return refentry::unif(rng); }
+double REF_SYM(rng_unif)(sgdnet_rng* rng) { return refentry::unif(rng); }
 
-const char* ref_last_error(void) { return refentry::g_err.c_str(); }
+const char* REF_SYM(last_error)(void) { return refentry::g_err.c_str(); }
 
-int ref_fit_dense(const double* x, int64_t n, int64_t p, const double* y, int32_t y_cols, const sgdnet_control* control,
+int REF_SYM(fit_dense)(const double* x, int64_t n, int64_t p, const double* y, int32_t y_cols, const sgdnet_control* control,
                   sgdnet_rng* rng, sgdnet_result* out) {
   return refentry::guarded(rng, n, [&] {
     Eigen::MatrixXd xm(n, p), ym(n, y_cols);
@@ -207,7 +213,7 @@ int ref_fit_dense(const double* x, int64_t n, int64_t p, const double* y, int32_
   });
 }
 
-int ref_fit_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x, int64_t n, int64_t p, const double* y,
+int REF_SYM(fit_sparse)(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x, int64_t n, int64_t p, const double* y,
                    int32_t y_cols, const sgdnet_control* control, sgdnet_rng* rng, sgdnet_result* out) {
   return refentry::guarded(rng, n, [&] {
     Eigen::SparseMatrix<double> xm(n, p, csc_p, csc_i, csc_x);
@@ -220,7 +226,7 @@ int ref_fit_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc
   });
 }
 
-void ref_result_free(sgdnet_result* r) {
+void REF_SYM(result_free)(sgdnet_result* r) {
   if (!r) return;
   std::free(r->a0); std::free(r->beta); std::free(r->lambda); std::free(r->dev_ratio);
   std::free(r->return_codes); std::free(r->epochs); std::free(r->losses); std::free(r->losses_ptr);

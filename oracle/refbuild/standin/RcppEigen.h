@@ -321,7 +321,7 @@ template <typename T>
 class SparseMatrix;
 
 struct SparseCol {
-  const Index* idx;
+  const int* idx;
   const double* val;
   Index nnz;
   Index len;
@@ -371,6 +371,12 @@ class SparseMatrix<double> {
   }
   Index rows() const { return r_; }
   Index cols() const { return c_; }
+  /* compressed-column storage access (StorageIndex = int, as in Eigen) */
+  bool isCompressed() const { return true; }
+  void makeCompressed() {}
+  const int* outerIndexPtr() const { return ptr_.data(); }
+  const int* innerIndexPtr() const { return idx_.data(); }
+  const double* valuePtr() const { return val_.data(); }
   SparseCol col(Index j) const {
     const Index s = ptr_[static_cast<size_t>(j)];
     return SparseCol{idx_.data() + s, val_.data() + s, ptr_[static_cast<size_t>(j) + 1] - s, r_};
@@ -391,7 +397,7 @@ class SparseMatrix<double> {
     Index e_, end_;
   };
 
-  std::vector<Index> ptr_, idx_;
+  std::vector<int> ptr_, idx_;
   std::vector<double> val_;
  private:
   Index r_, c_;
@@ -408,16 +414,16 @@ class SparseTransposed<double> {
     t.r_ = m_.c_;
     t.c_ = m_.r_;
     t.ptr_.assign(static_cast<size_t>(m_.r_) + 1, 0);
-    for (Index i : m_.idx_) ++t.ptr_[static_cast<size_t>(i) + 1];
+    for (int i : m_.idx_) ++t.ptr_[static_cast<size_t>(i) + 1];
     for (size_t i = 1; i < t.ptr_.size(); ++i) t.ptr_[i] += t.ptr_[i - 1];
     t.idx_.resize(m_.idx_.size());
     t.val_.resize(m_.val_.size());
-    std::vector<Index> fill(t.ptr_.begin(), t.ptr_.end() - 1);
+    std::vector<int> fill(t.ptr_.begin(), t.ptr_.end() - 1);
     for (Index j = 0; j < m_.c_; ++j)
       for (Index e = m_.ptr_[static_cast<size_t>(j)]; e < m_.ptr_[static_cast<size_t>(j) + 1]; ++e) {
         const Index i = m_.idx_[static_cast<size_t>(e)];
         const Index dst = fill[static_cast<size_t>(i)]++;
-        t.idx_[static_cast<size_t>(dst)] = j;
+        t.idx_[static_cast<size_t>(dst)] = static_cast<int>(j);
         t.val_[static_cast<size_t>(dst)] = m_.val_[static_cast<size_t>(e)];
       }
     return t;
@@ -487,6 +493,8 @@ class List {
 template <typename T>
 inline T as(const std::any& v) { return std::any_cast<T>(v); }
 
+[[noreturn]] inline void stop(const std::string& msg) { throw std::runtime_error(msg); }
+
 }  // namespace Rcpp
 
 /* ---------------------------------------------------------------- R's runif (R core nmath/runif.c) */
@@ -499,5 +507,8 @@ inline double runif(double a, double b) {
   return a + (b - a) * u;
 }
 }  // namespace R
+
+/* R API (R_ext/Random.h): one draw from R's global generator */
+inline double unif_rand() { return R::unif_rand_hook(); }
 
 #endif /* SGDNET_STANDIN_RCPPEIGEN_H_ */
