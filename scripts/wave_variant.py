@@ -44,3 +44,5 @@ if hasattr(lib.lib, "sgdnet_debug_wave_prof"):
     a = np.array(out[:], dtype=np.int64).reshape(20, 8)
     line += f" | chain per row: arithmetic {a[S + 1, 1] / n:.0f}, waits+reload {a[S + 1, 0] / n:.0f}, rows found not ready {100 * a[S + 1, 2] / n:.1f}%"
 print(line, flush=True)
+if os.environ.get("WAVE_VARIANT_ALL"):
+    print("  epoch ms:", " ".join(f"{v:.1f}" for v in times), flush=True)

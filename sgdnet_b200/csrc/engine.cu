@@ -166,6 +166,7 @@ struct Engine {
   int loss_blocks = 1;
   int sms = 148;
   int64_t max_rows_per_launch = 1;
+  bool trace_rounds = std::getenv("SGDNET_TRACE_ROUNDS") != nullptr;   // per-round device times on stderr
   size_t dense_smem = 0;
   unsigned dense_kts = 0, dense_pens = 0;   // class-count buckets / penalties present (dense kernel instantiations)
   Variant variant = Variant::Dense;
@@ -490,6 +491,7 @@ struct Engine {
       CK(cudaEventElapsedTime(&ms_dev, ev1, ev2));
       seconds_solver += ms_solver * 1e-3;
       seconds_dev += ms_dev * 1e-3;
+      if (trace_rounds) std::fprintf(stderr, "[sgdnet_b200] round: solver %.3f ms, passes %.3f ms, fits active %d\n", ms_solver, ms_dev, active);
       for (int i = 0; i < nf; ++i) {
         if (args_host[i].n_epochs == 0) continue;
         FitJob& j = jobs[i];
