@@ -181,3 +181,39 @@ def test_cuda_matches_reference_build_vectors(cuda, name):
     n_cmp = assert_matches_reference(sg.sgdnet(x, y, backend=cuda, **kw).raw, exp, exact=False)
     if name.startswith("fixed_"):
         assert n_cmp == len(exp["lambda_"])
+
+
+def test_edge_shapes(cuda, oracle):
+    """The shapes tests/test_ref_cpu.py::test_live_edge_cases pins against the reference's code, on the device:
+    all-zero and constant columns under standardisation, empty rows, a single feature, lambda = 0, an ascending user
+    path, a constant response (all-zero path), more features than samples."""
+    rng = np.random.default_rng(5)
+    n, p = 90, 7
+    x = rng.normal(size=(n, p)) * (rng.uniform(size=(n, p)) < 0.4)
+    x[:, 2] = 0.0
+    x[[3, 17, 40], :] = 0.0
+    x[:, 4] = 1.5
+    y = x @ rng.normal(size=p) + 0.1 * rng.normal(size=n)
+    yb = (y > np.median(y)).astype(float)
+    for std in (True, False):
+        for fam, yy in (("gaussian", y), ("binomial", yb)):
+            kw = dict(family=fam, alpha=0.6, standardize=std, nlambda=6, maxit=40, seed=3)
+            for xx in (x, sp.csc_matrix(x)):
+                g, r = both(cuda, oracle, xx, yy, **kw)
+                assert_fit_parity(g.raw, r.raw)
+    x1 = rng.normal(size=(60, 1))
+    y1 = 2.0 * x1[:, 0] + rng.normal(size=60)
+    for kw in (dict(family="gaussian", alpha=1.0, nlambda=5, seed=1), dict(family="gaussian", lambda_=[0.0], maxit=50, seed=1),
+               dict(family="gaussian", alpha=0.3, lambda_=[0.001, 0.01, 0.1, 1.0], maxit=30, seed=2)):
+        for xx in (x1, sp.csc_matrix(x1)):
+            g, r = both(cuda, oracle, xx, y1, **kw)
+            assert_fit_parity(g.raw, r.raw)
+    g, r = both(cuda, oracle, x1, np.full(60, 3.25), family="gaussian", nlambda=4, seed=1)
+    assert_fit_parity(g.raw, r.raw)
+    assert np.all(g.raw.lambda_ == 0) and np.all(g.raw.beta == 0)
+    xw = rng.normal(size=(25, 40))
+    yw = xw[:, :3] @ rng.normal(size=(3, 2)) + 0.1 * rng.normal(size=(25, 2))
+    g, r = both(cuda, oracle, xw, yw, family="mgaussian", nlambda=5, maxit=30, seed=4)
+    assert_fit_parity(g.raw, r.raw)
+    g, r = both(cuda, oracle, xw, np.arange(25) % 3, family="multinomial", alpha=0.5, nlambda=5, maxit=30, seed=4)
+    assert_fit_parity(g.raw, r.raw)

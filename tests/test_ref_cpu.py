@@ -108,3 +108,55 @@ def test_live_wscale_reset_path(ref, oracle_libm):
         b = sg.sgdnet(x, y, backend=ref, **kw).raw
         np.testing.assert_array_equal(a.beta, b.beta)
         np.testing.assert_array_equal(a.a0, b.a0)
+
+
+def _same(a, b, what):
+    for f in ("lambda_", "epochs", "return_codes", "beta", "a0", "dev_ratio"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f"{f} {what}")
+    assert (a.npasses, a.nulldev) == (b.npasses, b.nulldev), what
+
+
+def test_live_edge_cases_oracle_equals_reference_code(ref, oracle_libm):
+    """Shapes the reference's own tests poke at (tests/testthat/test-gaussian.R:62-71, test-sparse.R, test-lambda-path.R):
+    constant and all-zero columns under standardisation (sd == 0 -> 1, src/math.h:108, 128), empty rows, a single
+    feature, constant response (lambda_max == 0 -> all-zero path, src/utils.h:160-165), lambda = 0, a user path given
+    in ascending order, more features than samples."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    n, p = 90, 7
+    x = rng.normal(size=(n, p)) * (rng.uniform(size=(n, p)) < 0.4)
+    x[:, 2] = 0.0            # empty column
+    x[:, 4] = 1.5            # constant column
+    x[[3, 17, 40], :] = 0.0  # empty rows (column 4 included: it is then no longer constant, on purpose for one variant)
+    y = x @ rng.normal(size=p) + 0.1 * rng.normal(size=n)
+    yb = (y > np.median(y)).astype(float)
+    x2 = x.copy()
+    x2[:, 4] = 1.5           # truly constant column
+    for xm, tag in ((x, "empty rows"), (x2, "constant column")):
+        for std in (True, False):
+            for fam, yy in (("gaussian", y), ("binomial", yb)):
+                kw = dict(family=fam, alpha=0.6, standardize=std, nlambda=6, maxit=40, seed=3)
+                for xx in (xm, sp.csc_matrix(xm)):
+                    _same(sg.sgdnet(xx, yy, backend=oracle_libm, **kw).raw, sg.sgdnet(xx, yy, backend=ref, **kw).raw,
+                          f"{tag} std={std} {fam} sparse={sp.issparse(xx)}")
+    # a single feature; lambda = 0; ascending user path
+    x1 = rng.normal(size=(60, 1))
+    y1 = 2.0 * x1[:, 0] + rng.normal(size=60)
+    for kw in (dict(family="gaussian", alpha=1.0, nlambda=5, seed=1), dict(family="gaussian", lambda_=[0.0], maxit=50, seed=1),
+               dict(family="gaussian", alpha=0.3, lambda_=[0.001, 0.01, 0.1, 1.0], maxit=30, seed=2)):
+        for xx in (x1, sp.csc_matrix(x1)):
+            _same(sg.sgdnet(xx, y1, backend=oracle_libm, **kw).raw, sg.sgdnet(xx, y1, backend=ref, **kw).raw, str(kw))
+    # constant response: lambda_max == 0, every lambda 0, every coefficient 0 (test-gaussian.R:62-71)
+    yc = np.full(60, 3.25)
+    a = sg.sgdnet(x1, yc, backend=oracle_libm, family="gaussian", nlambda=4, seed=1).raw
+    b = sg.sgdnet(x1, yc, backend=ref, family="gaussian", nlambda=4, seed=1).raw
+    _same(a, b, "constant response")
+    assert np.all(b.lambda_ == 0) and np.all(b.beta == 0) and np.allclose(b.a0, 3.25)
+    # more features than samples (lambda.min.ratio 0.01 branch of R/sgdnet.R:191-192), mgaussian + multinomial
+    xw = rng.normal(size=(25, 40))
+    yw = xw[:, :3] @ rng.normal(size=(3, 2)) + 0.1 * rng.normal(size=(25, 2))
+    _same(sg.sgdnet(xw, yw, backend=oracle_libm, family="mgaussian", nlambda=5, maxit=30, seed=4).raw,
+          sg.sgdnet(xw, yw, backend=ref, family="mgaussian", nlambda=5, maxit=30, seed=4).raw, "n < p mgaussian")
+    yk = np.arange(25) % 3
+    _same(sg.sgdnet(xw, yk, backend=oracle_libm, family="multinomial", alpha=0.5, nlambda=5, maxit=30, seed=4).raw,
+          sg.sgdnet(xw, yk, backend=ref, family="multinomial", alpha=0.5, nlambda=5, maxit=30, seed=4).raw, "n < p multinomial")
