@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 NNZ_ROW = 100
+OUT = sys.stdout
 B_UPD = 12 * NNZ_ROW + 8 + 4 + 8 * 1 + 16 * 1          # 1236 B per sample-update
 
 
@@ -48,7 +49,8 @@ def parse():
     ap.add_argument("--cols", dest="p", type=int, default=100_000, help="p (columns of X)")
     ap.add_argument("--lambda-ind", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the bounded oracle sample")
-    ap.add_argument("--e2e-epochs", type=int, default=16, help="epochs of the bounded sgdnet_fit_sparse call of the e2e leg")
+    ap.add_argument("--e2e-epochs", type=int, default=48,
+                    help="epochs of the bounded sgdnet_fit_sparse call of the e2e leg (the whole 100-lambda path of this workload is 381)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -172,7 +174,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": n * raw.npasses / wall, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def path_lambda(lib, x, y, ind):
@@ -194,6 +196,10 @@ def config_dict(args, n_used=None):
 
 def main():
     args = parse()
+    # ONE JSON line on stdout: libraries (NCCL prints its version banner to fd 1) are sent to stderr
+    global OUT
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -323,7 +329,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args),
                 "device_ms_per_step": dev_s / args.steps * 1e3, "value_device_only": updates / dev_s,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
