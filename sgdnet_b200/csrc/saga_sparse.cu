@@ -559,26 +559,6 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) ld_state(st + jr[c], wr[c], gr[c], lr[c]);
       const double gm_early = f.gmem[m.s];
-#ifdef SGD_WAVE_PREFETCH
-      // ---- this worker's next row (t + S) is normally in the ring already: pull its feature records towards the SM
-      // now, a whole row time ahead of their gather (a hint only: no value is taken from it)
-      {
-        const uint32_t qn = q + S;
-        const int slot_n = static_cast<int>(qn % kWSlots);
-        const bool there = t + S < n && mbar_test_wait(&sm.full[slot_n], (qn / kWSlots) & 1u);
-        if (__all_sync(0xffffffffu, there)) {
-          const int nnz_n = sm.meta[slot_n].nnz;
-          if (nnz_n <= kCap) {
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-              const int e = c * 32 + lane;
-              const int jn = (e < nnz_n) ? sm.idx[slot_n][e] : 0;
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(st + jn));
-            }
-          }
-        }
-      }
-#endif
       // distance to the nearest row in flight that touches the feature; a reset row in the window touches all
       bool late = false;
 #pragma unroll

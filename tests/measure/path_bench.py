@@ -1,7 +1,7 @@
 """lambda-path fit time (BASELINE metric ii) at config 2's full size, bounded to the first L values of the automatic
 100-lambda path (warm-started, thresh = 1e-3): one sgdnet_fit_sparse call through the C ABI, host buffers in, archives
 out. With --cpu the oracle (libm arithmetic, one core) runs the same call for comparison.
-Usage: python scripts/path_bench.py [L] [--cpu]"""
+Usage: python tests/measure/path_bench.py [L] [--cpu]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import sgdnet_b200 as sg

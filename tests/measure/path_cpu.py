@@ -1,7 +1,7 @@
 """The same 100-lambda path of config 2 at FULL size on the CPU: the restated oracle in libm arithmetic (bit-identical to
 the reference's compiled sources, tests/test_ref_cpu.py) or, with --ref, oracle/_ref itself (the reference's own
 src/sgdnet.cpp; returns npasses but no per-lambda epochs). One core: the reference is single-threaded. Takes the better
-part of an hour. Usage: python scripts/path_cpu.py [--ref] [OUT.json]"""
+part of an hour. Usage: python tests/measure/path_cpu.py [--ref] [OUT.json]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import sgdnet_b200 as sg
