@@ -295,6 +295,22 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
   }
 }
 
+#ifdef SGD_WAVE_TRACE
+// Timeline trace (measurement build only): clock64 of eight events per row for rows [kTraceFrom, kTraceFrom + kTraceRows)
+// of the first epoch of a launch, written straight to global memory by one lane (fire-and-forget stores).
+//  0 chain: row taken up   1 chain: gok published   2 chain: next row's operands in hand
+//  3 worker: row in the ring (full)   4 worker: state gathered and caught up   5 worker: rdy published
+//  6 worker: gok seen   7 worker: row complete (done)          plus [8] nearest conflict distance, [9] next_ready
+constexpr uint32_t kTraceFrom = 50000, kTraceRows = 4096;
+__device__ long long g_wave_trace[kTraceRows][10];
+#define TRACE(ev, t_) do { if ((t_) - kTraceFrom < kTraceRows && ep_trace) g_wave_trace[(t_) - kTraceFrom][ev] = clock64(); } while (0)
+#define TRACEV(ev, t_, v_) do { if ((t_) - kTraceFrom < kTraceRows && ep_trace) g_wave_trace[(t_) - kTraceFrom][ev] = (v_); } while (0)
+extern "C" void sgdnet_debug_wave_trace(long long* out) { cudaMemcpyFromSymbol(out, g_wave_trace, sizeof(g_wave_trace)); }
+#else
+#define TRACE(ev, t_)
+#define TRACEV(ev, t_, v_)
+#endif
+
 #ifdef SGD_WAVE_PROF
 __device__ long long g_wave_prof[20][8];
 __device__ long long g_wave_stall[16][2];
@@ -416,6 +432,9 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
                                         double& b_io, double& gsi_io PROF_ARG) {
   const uint32_t n = k.n;
   const double nd = k.nd, rn = 1.0 / k.nd, gamma = k.gamma;
+#ifdef SGD_WAVE_TRACE
+  const bool ep_trace = q_base == 0u && lane == 0;
+#endif
   double b_reg = b_io, gsi_reg = gsi_io;
   double* __restrict__ gmem = f.gmem;
   const bool lead = lane == 0;
@@ -437,6 +456,7 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
   for (uint32_t t = 0; t < n; ++t) {
     const uint32_t q = q_base + t;
     const uint32_t n8 = ((q + 1u) % kSeq) * 8u, par1 = ((q + 1u) / kSeq) & 1u;
+    TRACE(0, t);
     PROF_T(c1);
     // probe the next row's operands while this row's arithmetic runs (non-blocking; the ring has a spare barrier
     // phase, so probing one row past the epoch's end is harmless)
@@ -456,6 +476,8 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
     sts_f64(a_gch + o8, gch);
     gmem[s] = g;
     mbar_arrive_if(lead, a_gok + o8);
+    TRACE(1, t);
+    TRACEV(9, t, next_ready ? 1 : 0);
     if (INTERCEPT) {
       const double gn = div_by_n(gch, nd, rn);
       gsi_reg += gn;
@@ -477,6 +499,9 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
     ya = ya_n;
     gm = gm_n;
     s = s_n;
+#ifdef SGD_WAVE_TRACE
+    if ((t) - kTraceFrom < kTraceRows && ep_trace) g_wave_trace[(t) - kTraceFrom][2] = (dot != 12345.678) ? clock64() : 0;
+#endif
 #ifdef SGD_WAVE_PROF
     const long long c3 = (dot != 12345.678) ? clock64() : 0;
     PROF_ADD(0, c2, c3);
@@ -503,6 +528,9 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
   FeatState* __restrict__ st = k.st;
   const int p = k.p;
 
+#ifdef SGD_WAVE_TRACE
+  const bool ep_trace = q_base == 0u && lane == 0;
+#endif
   double ws = 1.0;        // wscale at the start of step t_sim (before that step's reset test)
   uint32_t t_sim = 0;
   for (uint32_t t = warp; t < n; t += S) {
@@ -535,6 +563,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
     PROF_T(w1);
     PROF_ADD(0, w0, w1);
+    TRACE(3, t);
     const WaveSlotMeta m = sm.meta[slot];
     const bool serial = reset_here || m.nnz > kCap;
     const double ya = (k.family == kBinomial) ? 1.0 - m.y : m.y;
@@ -582,6 +611,11 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       };
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) wr[c] = caught_up(wr[c], gr[c], lr[c]);
+#ifdef SGD_WAVE_TRACE
+      if ((t) - kTraceFrom < kTraceRows && ep_trace) {
+        g_wave_trace[t - kTraceFrom][4] = (wr[0] + wr[1] + wr[2] + wr[3] != 12345.678) ? clock64() : 0;
+      }
+#endif
       double gm = gm_early;
       // ---- rows in flight. A feature that row t-d (d < S) also holds is not read from HBM: as soon as the chain
       // warp has published that row's g_change, this warp repeats the row's own coefficient step on the state it
@@ -597,23 +631,27 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       }
       need_g = __reduce_or_sync(0xffffffffu, need_g) | ((m.dup != 0) ? (1u << m.dup) : 0u);
       need_f = __reduce_or_sync(0xffffffffu, need_f);
-      if ((need_g | need_f) != 0) {
-        // oldest first: those are complete already, the nearest row is the one worth sleeping on
-        for (uint32_t rest = need_f; rest != 0;) {
-          const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
-          rest &= ~(1u << d);
-          wait_row(sm.fdone, q - d);
+      TRACEV(8, t, static_cast<long long>(need_g | (need_f << 16)));
+      auto forward_stores = [&]() {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          sm.fw_w[sq][c * 32 + lane] = wr[c];
+          sm.fw_g[sq][c * 32 + lane] = gr[c];
+          sm.fw_x[sq][c * 32 + lane] = vr[c];
         }
-        for (uint32_t rest = need_g; rest != 0;) {
-          const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
-          rest &= ~(1u << d);
-          wait_row(sm.gok, q - d);
+        if (!IDENT && lane == 0) {
+          sm.c_sc[sq] = sc;
+          sm.c_step1[sq] = step1;
+          sm.c_thr1[sq] = thr1;
         }
-        if (m.dup != 0) gm = f.gmem[m.s];
+      };
+      // the coefficient step of row t-d redone on its forwarded state for this lane's entries (all of them, or all
+      // but those at distance `skip_d`), caught up to this row
+      auto apply_forward = [&](uint32_t skip_d) {
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const uint32_t d = dr[c] & 15u, sqd = (q - d) % kSeq, pos = (dr[c] >> 4) & 127u;
-          const bool fwd = dr[c] != 0 && (dr[c] & kCodeGlobal) == 0;
+          const bool fwd = dr[c] != 0 && (dr[c] & kCodeGlobal) == 0 && d != skip_d;
           const double gx = sm.fw_x[sqd][pos] * sm.q_gch[sqd];
           const double fg = sm.fw_g[sqd][pos];
           const double w_new = penalty_k1<PEN>(sm.fw_w[sqd][pos] + gx * (IDENT ? sc : sm.c_sc[sqd]), fg,
@@ -622,72 +660,166 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
           wr[c] = fwd ? caught_up(w_new, g_new, t - d + 1u) : wr[c];   // row t-d left lag = t-d+1
           gr[c] = fwd ? g_new : gr[c];
         }
-        if (need_f != 0) {                          // behind a serial row (rare): re-read HBM
+      };
+      bool published = false;
+#ifdef SGD_FAST_CONFLICT   // measured 612 -> 589 cycles per update (838 -> 698 at p = 30k) but NOT shipped: one stress
+                          // configuration (gaussian lasso, no intercept: the chain warp is then nearly free) still shows a
+                          // timing-dependent mismatch of the coefficients, although the published dot products equal the
+                          // full butterfly's on all 116 935 rows checked
+      if (need_g != 0 && need_f == 0 && m.dup == 0) {
+        // ---- fast conflict path. Timeline traces of this kernel show the serial cost of a conflict: from the moment
+        // the chain warp publishes the g_change a row waits for to the moment that row's dot product is published
+        // took about 1000 cycles (forward step on all four chunks, catch-up, twelve stores, the products and a full
+        // butterfly), all of it with the chain warp idle. When ONE position of the row is all that depends on the
+        // nearest unfinished row, everything else is done before the wait: the other rows' forwards, the forwarding
+        // stores, the running sums, and the butterfly with the late lane contributing nothing - what that lane
+        // RECEIVES in the five levels are sums that never include its own value, i.e. exactly the addends of
+        // ((((a + r1) + r2) + r3) + r4) + r5, the value every lane of the full butterfly ends with (each level adds
+        // the same two numbers, and addition commutes). After the wait only the late lane works: one forward step,
+        // at most four additions to close its running sum, five to close the butterfly, and it publishes.
+        uint32_t my_near = 16u;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const uint32_t d = dr[c] & 15u;
+          my_near = (dr[c] != 0 && d < my_near) ? d : my_near;
+        }
+        const uint32_t dnear = __reduce_min_sync(0xffffffffu, my_near);
+        int cnt = 0, c1 = 0;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const bool hit = dr[c] != 0 && (dr[c] & 15u) == dnear;
+          cnt += hit ? 1 : 0;
+          c1 = hit ? c : c1;
+        }
+        const bool fm_ok = true;
+        if (fm_ok && __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt)) == 1u) {
+          const bool late_lane = cnt == 1;
+          for (uint32_t rest = need_g & ~(1u << dnear); rest != 0;) {     // older rows: complete already
+            const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
+            rest &= ~(1u << d);
+            wait_row(sm.gok, q - d);
+          }
+          apply_forward(dnear);
+          forward_stores();                      // the late position is stored again below
+          double acc = 0.0, prod[kChunks];
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) {
-            if (dr[c] & kCodeGlobal) {
-              ld_state(st + jr[c], wr[c], gr[c], lr[c]);
-              wr[c] = caught_up(wr[c], gr[c], lr[c]);
+            prod[c] = vr[c] * wr[c];
+            const double a2 = acc + prod[c];
+            acc = (valid[c] && !(late_lane && c >= c1)) ? a2 : acc;
+          }
+          double v = late_lane ? 0.0 : acc;
+          double rc[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const double x = __shfl_xor_sync(0xffffffffu, v, 16 >> i);
+            rc[i] = x;
+            v = v + x;
+          }
+          // the late position's own operands
+          double x_late = vr[0];
+          uint32_t code1 = dr[0];
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            x_late = (c == c1) ? vr[c] : x_late;
+            code1 = (c == c1) ? dr[c] : code1;
+          }
+          const uint32_t sqd = (q - dnear) % kSeq, pos = (code1 >> 4) & 127u;
+          __syncwarp();                          // every lane's forwarding stores precede the late lane's arrive
+          wait_row(sm.gok, q - dnear);
+          if (late_lane) {
+            // (that row's forwarded state is only guaranteed once its gok is: it is stored ahead of its rdy)
+            const double fwx = sm.fw_x[sqd][pos], fwg = sm.fw_g[sqd][pos], fww = sm.fw_w[sqd][pos];
+            const double sc_p = IDENT ? sc : sm.c_sc[sqd];
+            const double step1_p = IDENT ? step1 : sm.c_step1[sqd];
+            const double thr1_p = IDENT ? thr1 : sm.c_thr1[sqd];
+            const double gx = fwx * sm.q_gch[sqd];
+            const double w_new = penalty_k1<PEN>(fww + gx * sc_p, fwg, step1_p, thr1_p);
+            const double g_new = fwg + gx * sc2;
+            const double w_c = caught_up(w_new, g_new, t - dnear + 1u);
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+              wr[c] = (c == c1) ? w_c : wr[c];
+              gr[c] = (c == c1) ? g_new : gr[c];
             }
+            sm.fw_w[sq][c1 * 32 + lane] = w_c;
+            sm.fw_g[sq][c1 * 32 + lane] = g_new;
+            double a = acc + x_late * w_c;
+#pragma unroll
+            for (int c = 1; c < kChunks; ++c) {
+              const double a2 = a + prod[c];
+              a = (c > c1 && valid[c]) ? a2 : a;
+            }
+            a = a + rc[0];
+            a = a + rc[1];
+            a = a + rc[2];
+            a = a + rc[3];
+            a = a + rc[4];
+            sm.q_dot[sq] = IDENT ? a : a * ws;
+            sm.q_ya[sq] = ya;
+            sm.q_gm[sq] = gm;
+            sm.q_s[sq] = m.s;
+            mbar_arrive(&sm.rdy[sq]);
           }
           __syncwarp();
+          published = true;
         }
       }
-      // ---- forward this row's caught-up state (read by the rows that conflict with it, after its gok)
+#endif
+      if (!published) {
+        if ((need_g | need_f) != 0) {
+          // oldest first: those are complete already, the nearest row is the one worth sleeping on
+          for (uint32_t rest = need_f; rest != 0;) {
+            const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
+            rest &= ~(1u << d);
+            wait_row(sm.fdone, q - d);
+          }
+          for (uint32_t rest = need_g; rest != 0;) {
+            const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
+            rest &= ~(1u << d);
+            wait_row(sm.gok, q - d);
+          }
+          if (m.dup != 0) gm = f.gmem[m.s];
+          apply_forward(16u);
+          if (need_f != 0) {                          // behind a serial row (rare): re-read HBM
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        sm.fw_w[sq][c * 32 + lane] = wr[c];
-        sm.fw_g[sq][c * 32 + lane] = gr[c];
-        sm.fw_x[sq][c * 32 + lane] = vr[c];
-      }
-      if (!IDENT && lane == 0) {
-        sm.c_sc[sq] = sc;
-        sm.c_step1[sq] = step1;
-        sm.c_thr1[sq] = thr1;
-      }
-      PROF_T(w3);
-      PROF_ADD(2, w2, w3);
-#ifdef SGD_WAVE_PROF
-      {
-        long long tw = clock64();
-        for (int o = 16; o > 0; o >>= 1) tw = max(tw, __shfl_xor_sync(0xffffffffu, tw, o));
-        if (lane == 0) sm.ts_wake[sq] = tw;
-      }
-#endif
-      // ---- the sparse dot product: position e -> running sum e mod 32, then the butterfly (sgdnet_arith.h)
-      double acc = 0.0;
+            for (int c = 0; c < kChunks; ++c) {
+              if (dr[c] & kCodeGlobal) {
+                ld_state(st + jr[c], wr[c], gr[c], lr[c]);
+                wr[c] = caught_up(wr[c], gr[c], lr[c]);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        // ---- forward this row's caught-up state (read by the rows that conflict with it, after its gok)
+        forward_stores();
+        PROF_T(w3);
+        PROF_ADD(2, w2, w3);
+        // ---- the sparse dot product: position e -> running sum e mod 32, then the butterfly (sgdnet_arith.h)
+        double acc = 0.0;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const double a2 = acc + vr[c] * wr[c];
-        acc = valid[c] ? a2 : acc;
+        for (int c = 0; c < kChunks; ++c) {
+          const double a2 = acc + vr[c] * wr[c];
+          acc = valid[c] ? a2 : acc;
+        }
+        double dot = warp_sum(acc);
+        if (!IDENT) dot = dot * ws;
+        __syncwarp();                                 // the forwarded state of every lane precedes the arrive
+        if (lane == 0) {
+          sm.q_dot[sq] = dot;
+          sm.q_ya[sq] = ya;
+          sm.q_gm[sq] = gm;
+          sm.q_s[sq] = m.s;
+          mbar_arrive(&sm.rdy[sq]);
+        }
       }
-#ifdef SGD_WAVE_PROF
-      if (lane == 0) sm.ts_a[sq] = (acc != 12345.678) ? clock64() : 0;
-#endif
-      double dot = warp_sum(acc);
-      if (!IDENT) dot = dot * ws;
-#ifdef SGD_WAVE_PROF
-      if (lane == 0) sm.ts_b[sq] = (dot != 12345.678) ? clock64() : 0;
-      uint32_t dmin = 16;
-      for (int c = 0; c < kChunks; ++c) if (dr[c] != 0) dmin = min(dmin, dr[c] & 15u);
-      for (int o = 16; o > 0; o >>= 1) dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-      if (lane == 0) sm.q_dmin[sq] = dmin & 15u;
-#endif
-      __syncwarp();                                 // the forwarded state of every lane precedes the arrive
-      if (lane == 0) {
-        sm.q_dot[sq] = dot;
-        sm.q_ya[sq] = ya;
-        sm.q_gm[sq] = gm;
-        sm.q_s[sq] = m.s;
-#ifdef SGD_WAVE_PROF
-        sm.ts_rdy[sq] = clock64();
-#endif
-        mbar_arrive(&sm.rdy[sq]);
-      }
+      TRACE(5, t);
       PROF_T(w4);
       PROF_ADD(3, w3, w4);
       wait_row(sm.gok, q);
       const double gch = sm.q_gch[sq];
+      TRACE(6, t);
       PROF_T(w5);
       PROF_ADD(4, w4, w5);
 #ifdef SGD_WAVE_PROF
@@ -775,6 +907,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       if (t > 0) wait_row(sm.done, q - 1u);
       mbar_arrive(&sm.done[sq]);
     }
+    TRACE(7, t);
     PROF_T(w7);
     PROF_ADD(5, w1, w6);
     PROF_ADD(6, w6, w7);
