@@ -662,10 +662,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
         }
       };
       bool published = false;
-#ifdef SGD_FAST_CONFLICT   // measured 612 -> 589 cycles per update (838 -> 698 at p = 30k) but NOT shipped: one stress
-                          // configuration (gaussian lasso, no intercept: the chain warp is then nearly free) still shows a
-                          // timing-dependent mismatch of the coefficients, although the published dot products equal the
-                          // full butterfly's on all 116 935 rows checked
+#ifndef SGD_NO_FAST_CONFLICT
       if (need_g != 0 && need_f == 0 && m.dup == 0) {
         // ---- fast conflict path. Timeline traces of this kernel show the serial cost of a conflict: from the moment
         // the chain warp publishes the g_change a row waits for to the moment that row's dot product is published
@@ -825,6 +822,12 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
 #ifdef SGD_WAVE_PROF
       if (lane == 0) sm.ts_gokwake[sq] = w5;
 #endif
+      // ---- write-after-write order in HBM: a feature this row shares with a row still in flight is scattered by
+      // both, and the earlier row's record has to land first. `done` is chained in row order, so the nearest needed
+      // row's `done` covers every needed row; it has normally completed long before (one probe, behind the publish, off
+      // the chain warp's path). Found with the fast conflict path: without this wait the order only held because a
+      // conflicting row used to publish its dot product ~1000 cycles after the g_change of the row it waited for.
+      if (need_g != 0) wait_row(sm.done, q - static_cast<uint32_t>(__ffs(static_cast<int>(need_g)) - 1));
       // ---- AddWeighted(w), LaggedUpdate(k = t+1, lag 1), AddWeighted(g_sum), scatter
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
