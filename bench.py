@@ -270,10 +270,10 @@ def main():
     achieved = n * B_UPD / per_launch_s / 1e9
     traffic, traffic_src = None, None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
-        with open(os.path.join(ROOT, "profiles", "r1_09_wave_final_ncu_summary.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r1_12_wave_fastpath_ncu_summary.json")) as fh:
             prof = json.load(fh)
         if n == prof["updates_per_launch"]:
-            traffic, traffic_src = prof["dram_bytes_per_launch"], "profiles/r1_09_wave_final_ncu_summary.json"
+            traffic, traffic_src = prof["dram_bytes_per_launch"], "profiles/r1_12_wave_fastpath_ncu_summary.json"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "saga_sparse_wave_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
