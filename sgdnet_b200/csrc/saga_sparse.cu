@@ -143,10 +143,6 @@ struct __align__(128) WaveSmem {
   double q_gm[kSeq];      //                  gradient memory of the sample
   double q_gch[kSeq];     // chain -> worker: g_change
   uint32_t q_s[kSeq];     // worker -> chain: sample id
-#ifdef SGD_WAVE_PROF
-  uint32_t q_dmin[kSeq];
-  long long ts_gok[kSeq], ts_fdone[kSeq], ts_wake[kSeq], ts_rdy[kSeq], ts_gokwake[kSeq], ts_a[kSeq], ts_b[kSeq], ts_c[kSeq];
-#endif
   double red[2 * 32];
   double wscale_s;
 };
@@ -311,20 +307,6 @@ extern "C" void sgdnet_debug_wave_trace(long long* out) { cudaMemcpyFromSymbol(o
 #define TRACEV(ev, t_, v_)
 #endif
 
-#ifdef SGD_WAVE_PROF
-__device__ long long g_wave_prof[20][8];
-__device__ long long g_wave_stall[16][2];
-__device__ long long g_wave_path[12];
-#define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(slot, a, b) prof_acc[slot] += (b) - (a)
-#define PROF_ARG , long long* prof_acc
-#define PROF_PASS , prof_acc
-#else
-#define PROF_T(var)
-#define PROF_ADD(slot, a, b)
-#define PROF_ARG
-#define PROF_PASS
-#endif
 
 // A taken branch costs a lone warp about 23 cycles on sm_100a (scripts/microbench.cu: a dependent DFMA is 8), and the
 // solver is a handful of lone warps, so the hot paths below are written to compile to straight-line predicated code:
@@ -429,7 +411,7 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
 // lp = dot + b; Gradient (src/families.h:89-96, 161-168); g_change; intercept step (src/saga-sparse.h:300-304).
 template <int FAMILY, bool INTERCEPT>
 __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const WaveConst& k, uint32_t q_base, int lane,
-                                        double& b_io, double& gsi_io PROF_ARG) {
+                                        double& b_io, double& gsi_io) {
   const uint32_t n = k.n;
   const double nd = k.nd, rn = 1.0 / k.nd, gamma = k.gamma;
 #ifdef SGD_WAVE_TRACE
@@ -445,10 +427,7 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
   const uint32_t a_dot = sb + offsetof(WaveSmem, q_dot), a_ya = sb + offsetof(WaveSmem, q_ya);
   const uint32_t a_gm = sb + offsetof(WaveSmem, q_gm), a_gch = sb + offsetof(WaveSmem, q_gch);
   const uint32_t a_s = sb + offsetof(WaveSmem, q_s);
-  PROF_T(c00);
   wait_row(sm.rdy, q_base);
-  PROF_T(c01);
-  PROF_ADD(0, c00, c01);
   uint32_t o8 = (q_base % kSeq) * 8u;
   double dot = lds_f64(a_dot + o8), ya = lds_f64(a_ya + o8), gm = lds_f64(a_gm + o8);
   uint32_t s = lds_u32(a_s + (o8 >> 1));
@@ -457,7 +436,6 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
     const uint32_t q = q_base + t;
     const uint32_t n8 = ((q + 1u) % kSeq) * 8u, par1 = ((q + 1u) / kSeq) & 1u;
     TRACE(0, t);
-    PROF_T(c1);
     // probe the next row's operands while this row's arithmetic runs (non-blocking; the ring has a spare barrier
     // phase, so probing one row past the epoch's end is harmless)
     const bool next_ready = mbar_test_wait_a(a_rdy + n8, par1);
@@ -483,10 +461,6 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
       gsi_reg += gn;
       b_reg -= gamma * (gsi_reg * 0.01 + gn);
     }
-#ifdef SGD_WAVE_PROF
-    const long long c2 = (b_reg != 12345.678) ? clock64() : 0;
-    PROF_ADD(1, c1, c2);
-#endif
     if (__builtin_expect(!next_ready && t + 1u < n, 0)) {
       mbar_wait_a(a_rdy + n8, par1);
       dot_n = lds_f64(a_dot + n8);
@@ -502,15 +476,6 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
 #ifdef SGD_WAVE_TRACE
     if ((t) - kTraceFrom < kTraceRows && ep_trace) g_wave_trace[(t) - kTraceFrom][2] = (dot != 12345.678) ? clock64() : 0;
 #endif
-#ifdef SGD_WAVE_PROF
-    const long long c3 = (dot != 12345.678) ? clock64() : 0;
-    PROF_ADD(0, c2, c3);
-    if (t + 1u < n && lead) {
-      const uint32_t dm = sm.q_dmin[(q + 1u) % kSeq];
-      g_wave_stall[dm][0] += 1;
-      g_wave_stall[dm][1] += c3 - c2;
-    }
-#endif
   }
   b_io = b_reg;
   gsi_io = gsi_reg;
@@ -521,7 +486,7 @@ __device__ __noinline__ void wave_chain(WaveSmem& sm, const FitDev& f, const Wav
 // lag_scaling[m] is exactly m, and every "/ wscale" is a division by 1.0 (exact, skipped).
 template <int S, int PEN, bool IDENT>
 __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const WaveConst& k, uint32_t q_base, int warp,
-                                         int lane PROF_ARG) {
+                                         int lane) {
   const uint32_t n = k.n;
   const double gamma = k.gamma, r = k.r, sc2 = k.sc2, bg = k.bg;
   const double* __restrict__ ls_table = k.ls_table;
@@ -559,10 +524,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       thr1 = bg / ws_next;
     }
 
-    PROF_T(w0);
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
-    PROF_T(w1);
-    PROF_ADD(0, w0, w1);
     TRACE(3, t);
     const WaveSlotMeta m = sm.meta[slot];
     const bool serial = reset_here || m.nnz > kCap;
@@ -598,8 +560,6 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
         dr[c] = d;
         late = late || d != 0;
       }
-      PROF_T(w2);
-      PROF_ADD(1, w1, w2);
       // LaggedUpdate(k = t) on one gathered feature (src/saga-sparse.h:76-100, src/penalties.h); the result is only
       // taken when the lag is non-zero, exactly like the reference's `if (lagged_amount != 0)`
       auto caught_up = [&](double w, double g, uint32_t lg) {
@@ -791,8 +751,6 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
         }
         // ---- forward this row's caught-up state (read by the rows that conflict with it, after its gok)
         forward_stores();
-        PROF_T(w3);
-        PROF_ADD(2, w2, w3);
         // ---- the sparse dot product: position e -> running sum e mod 32, then the butterfly (sgdnet_arith.h)
         double acc = 0.0;
 #pragma unroll
@@ -812,16 +770,9 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
         }
       }
       TRACE(5, t);
-      PROF_T(w4);
-      PROF_ADD(3, w3, w4);
       wait_row(sm.gok, q);
       const double gch = sm.q_gch[sq];
       TRACE(6, t);
-      PROF_T(w5);
-      PROF_ADD(4, w4, w5);
-#ifdef SGD_WAVE_PROF
-      if (lane == 0) sm.ts_gokwake[sq] = w5;
-#endif
       // ---- write-after-write order in HBM: a feature this row shares with a row still in flight is scattered by
       // both, and the earlier row's record has to land first. `done` is chained in row order, so the nearest needed
       // row's `done` covers every needed row; it has normally completed long before (one probe, behind the publish, off
@@ -861,9 +812,6 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       double dot = warp_sum(acc);
       if (!IDENT) dot = dot * ws;
       if (lane == 0) {
-#ifdef SGD_WAVE_PROF
-        sm.q_dmin[sq] = 15;
-#endif
         sm.q_dot[sq] = dot;
         sm.q_ya[sq] = ya;
         sm.q_gm[sq] = gm;
@@ -901,19 +849,12 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
     }
     // ---- completion chained in row order: the row's HBM scatter is visible and so is every earlier row's
     __syncwarp();
-    PROF_T(w6);
     if (lane == 0) {
-#ifdef SGD_WAVE_PROF
-      sm.ts_fdone[sq] = clock64();
-#endif
       mbar_arrive(&sm.fdone[sq]);
       if (t > 0) wait_row(sm.done, q - 1u);
       mbar_arrive(&sm.done[sq]);
     }
     TRACE(7, t);
-    PROF_T(w7);
-    PROF_ADD(5, w1, w6);
-    PROF_ADD(6, w6, w7);
     ws = ws_next;
     t_sim = t + 1u;
   }
@@ -992,9 +933,6 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
   __syncthreads();
 
   double b_reg = f.b[0], gsi_reg = f.gsi[0];   // live in the chain warp
-#ifdef SGD_WAVE_PROF
-  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
 
   uint32_t it_outer = pg.it_outer, epochs_done = 0;
   bool finished = false;
@@ -1007,19 +945,19 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
       // idle placeholder of the chain warp's scheduler
     } else if (role == -1) {
       if (k.family == kBinomial) {
-        if (k.fit_intercept) wave_chain<kBinomial, true>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
-        else wave_chain<kBinomial, false>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
+        if (k.fit_intercept) wave_chain<kBinomial, true>(sm, f, k, q_base, lane, b_reg, gsi_reg);
+        else wave_chain<kBinomial, false>(sm, f, k, q_base, lane, b_reg, gsi_reg);
       } else {
-        if (k.fit_intercept) wave_chain<kGaussian, true>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
-        else wave_chain<kGaussian, false>(sm, f, k, q_base, lane, b_reg, gsi_reg PROF_PASS);
+        if (k.fit_intercept) wave_chain<kGaussian, true>(sm, f, k, q_base, lane, b_reg, gsi_reg);
+        else wave_chain<kGaussian, false>(sm, f, k, q_base, lane, b_reg, gsi_reg);
       }
     } else {
       if (pen == kRidge) {
-        if (ident) wave_worker<S, kRidge, true>(sm, f, k, q_base, role, lane PROF_PASS);
-        else wave_worker<S, kRidge, false>(sm, f, k, q_base, role, lane PROF_PASS);
+        if (ident) wave_worker<S, kRidge, true>(sm, f, k, q_base, role, lane);
+        else wave_worker<S, kRidge, false>(sm, f, k, q_base, role, lane);
       } else {
-        if (ident) wave_worker<S, kElasticNet, true>(sm, f, k, q_base, role, lane PROF_PASS);
-        else wave_worker<S, kElasticNet, false>(sm, f, k, q_base, role, lane PROF_PASS);
+        if (ident) wave_worker<S, kElasticNet, true>(sm, f, k, q_base, role, lane);
+        else wave_worker<S, kElasticNet, false>(sm, f, k, q_base, role, lane);
       }
     }
     __syncthreads();
@@ -1052,10 +990,6 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
     finished = !free_run && (conv || !(it_outer < f.max_iter));
   }
 
-#ifdef SGD_WAVE_PROF
-  if (lane == 0 && warp < 20)
-    for (int i = 0; i < 8; ++i) g_wave_prof[warp][i] = prof_acc[i];
-#endif
   if (role == -1 && lane == 0) {
     f.b[0] = b_reg;
     f.gsi[0] = gsi_reg;
@@ -1263,14 +1197,6 @@ saga_sparse_generic_kernel(FitDev* __restrict__ fits, Progress* __restrict__ pro
   }
 }
 
-#ifdef SGD_WAVE_PROF
-extern "C" void sgdnet_debug_wave_prof(long long* out) { cudaMemcpyFromSymbol(out, g_wave_prof, sizeof(long long) * 160); }
-extern "C" void sgdnet_debug_wave_path(long long* out) { cudaMemcpyFromSymbol(out, g_wave_path, sizeof(long long) * 12); }
-extern "C" void sgdnet_debug_wave_stall(long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g_wave_stall, sizeof(long long) * 32);
-  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(g_wave_stall, z, sizeof(z)); }
-}
-#endif
 
 int wave_warps() {
   static int s = [] {
