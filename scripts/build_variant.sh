@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds sgdnet_b200/libsgdnet_b200_<NAME>.so: the library with saga_sparse.cu recompiled with extra -D flags
 # (measurement variants of the wavefront kernel; not part of the product build).
-# Usage: scripts/build_variant.sh NAME "-DSGD_WAVE_PROF_LIGHT ..."
+# Usage: scripts/build_variant.sh NAME "-DSGD_WAVE_TRACE"      (or -DSGD_NO_FAST_CONFLICT, ...)
 set -e
 NAME=$1; EXTRA=$2
 cd "$(dirname "$0")/.."

@@ -1,6 +1,5 @@
 """Epoch time of the sparse wavefront kernel for a measurement variant of the library
-(sgdnet_b200/libsgdnet_b200_<NAME>.so, scripts/build_variant.sh); with the light profile compiled in
-(-DSGD_WAVE_PROF_LIGHT) also the chain warp's cycles per row in arithmetic and in waits.
+(sgdnet_b200/libsgdnet_b200_<NAME>.so, scripts/build_variant.sh; NAME = product for the shipped library).
 Usage: python scripts/wave_variant.py NAME [n] [p] [epochs] [family] [intercept 0/1]"""
 import ctypes as C
 import os
@@ -38,11 +37,6 @@ for it in range(epochs):
 t = min(times[1:]) if len(times) > 1 else times[0]
 S = int(os.environ.get("SGDNET_WAVE_WARPS", "8"))
 line = f"{name} {family} intercept={int(icpt)} S={S} n={n} p={p}: epoch {t:.1f} ms = {t * 1e-3 * 1.965e9 / n:.0f} cycles/row, {n / t / 1e3:.3f} M updates/s"
-if hasattr(lib.lib, "sgdnet_debug_wave_prof"):
-    out = (C.c_longlong * 160)()
-    lib.lib.sgdnet_debug_wave_prof(out)
-    a = np.array(out[:], dtype=np.int64).reshape(20, 8)
-    line += f" | chain per row: arithmetic {a[S + 1, 1] / n:.0f}, waits+reload {a[S + 1, 0] / n:.0f}, rows found not ready {100 * a[S + 1, 2] / n:.1f}%"
 print(line, flush=True)
 if os.environ.get("WAVE_VARIANT_ALL"):
     print("  epoch ms:", " ".join(f"{v:.1f}" for v in times), flush=True)
