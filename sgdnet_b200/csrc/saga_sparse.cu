@@ -693,7 +693,8 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
             const double gx = fwx * sm.q_gch[sqd];
             const double w_new = penalty_k1<PEN>(fww + gx * sc_p, fwg, step1_p, thr1_p);
             const double g_new = fwg + gx * sc2;
-            const double w_c = caught_up(w_new, g_new, t - dnear + 1u);
+            // the row right before this one left lag = t: nothing to catch up (caught_up would return w_new itself)
+            const double w_c = (dnear == 1u) ? w_new : caught_up(w_new, g_new, t - dnear + 1u);
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
               wr[c] = (c == c1) ? w_c : wr[c];
