@@ -73,3 +73,33 @@ def test_soft_threshold_select_form_equals_the_reference_form():
     nan = np.isnan(ref)
     np.testing.assert_array_equal(nan, np.isnan(alt))
     np.testing.assert_array_equal(ref[~nan].view(np.int64), alt[~nan].view(np.int64))
+
+
+def test_late_lane_butterfly_identity():
+    """The fast conflict path of the wavefront kernel (saga_sparse.cu) closes a row's dot product from ONE lane: it runs
+    the 32-lane xor-butterfly with that lane contributing nothing, keeps what the lane RECEIVES at the five levels, and
+    later forms ((((a + r1) + r2) + r3) + r4) + r5 with the lane's real running sum a. That must be the bits every lane
+    of the full butterfly ends with (sgdnet_arith.h, item 2), for every lane and any values."""
+    rng = np.random.default_rng(7)
+
+    def butterfly(v):
+        v = np.array(v, dtype=np.float64)
+        received = np.zeros((5, 32))
+        for i, o in enumerate((16, 8, 4, 2, 1)):
+            x = v[np.arange(32) ^ o]
+            received[i] = x
+            v = v + x
+        return v, received
+
+    for trial in range(200):
+        a = rng.normal(size=32) * 10.0 ** rng.integers(-8, 8, size=32)
+        full, _ = butterfly(a)
+        assert np.all(full == full[0])                      # every lane ends with the same bits
+        lane = int(rng.integers(0, 32))
+        dry = a.copy()
+        dry[lane] = 0.0
+        _, rc = butterfly(dry)
+        closed = a[lane]
+        for i in range(5):
+            closed = closed + rc[i, lane]
+        assert closed == full[0]
