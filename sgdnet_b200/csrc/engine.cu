@@ -66,6 +66,9 @@ struct Arena {
     size_t size = 0, used = 0;
   };
   std::vector<Slab> dev, pin;
+  Arena() = default;
+  Arena(const Arena&) = delete;              // owns raw device / pinned pointers
+  Arena& operator=(const Arena&) = delete;
   static constexpr size_t kAlign = 256;
   static constexpr size_t kDevSlab = size_t(128) << 20, kPinSlab = size_t(8) << 20;
 
