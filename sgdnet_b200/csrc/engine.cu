@@ -591,8 +591,9 @@ struct Engine {
     a.a0 = a0_dev;
     a.beta = beta_dev;
     a.link = link_dev;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(int64_t(sms) * 4, (n_rows + 7) / 8)));
     a.partials = arena.alloc<double>(size_t(blocks) * L);
     a.score = score_dev;
