@@ -19,6 +19,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -66,6 +67,8 @@ struct Arena {
     size_t size = 0, used = 0;
   };
   std::vector<Slab> dev, pin;
+  cudaStream_t stream = nullptr;             // zero-fills are ordered on the engine's stream (it is non-blocking: the
+                                             // legacy default stream would not be ordered with it)
   Arena() = default;
   Arena(const Arena&) = delete;              // owns raw device / pinned pointers
   Arena& operator=(const Arena&) = delete;
@@ -94,7 +97,7 @@ struct Arena {
   T* alloc(size_t count, bool zero = true) {
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     void* p = carve(dev, bytes, kDevSlab, false);
-    if (zero) CK(cudaMemset(p, 0, bytes));
+    if (zero) CK(cudaMemsetAsync(p, 0, bytes, stream));
     return static_cast<T*>(p);
   }
   template <typename T>
@@ -187,6 +190,7 @@ struct Engine {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) throw CudaFail{e == cudaSuccess ? cudaErrorNoDevice : e, "no CUDA device (no CPU fallback)"};
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    arena.stream = stream;
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventCreate(&ev2));
@@ -322,17 +326,21 @@ struct Engine {
     const FitJob& j0 = jobs[0];
     if (!j0.dev.sparse) variant = Variant::Dense;
     else variant = (j0.dev.K == 1 && !j0.dev.standardize) ? Variant::SparseK1 : Variant::SparseGeneric;
-    int max_p = 0, max_ld = 0, max_K = 0;
     int64_t max_n = 0;
-    for (auto& j : jobs) {
-      max_p = std::max(max_p, j.dev.p);
-      max_ld = std::max(max_ld, j.dev.ld);
-      max_K = std::max(max_K, j.dev.K);
-      max_n = std::max(max_n, j.dev.n);
-    }
+    for (auto& j : jobs) max_n = std::max(max_n, j.dev.n);
     if (variant == Variant::Dense) {
-      int in_smem = 0;
-      dense_smem = dense_smem_bytes(max_K, max_p, max_ld, &in_smem);
+      // the launch's dynamic shared memory: what the most demanding fit of the batch needs (each CTA decides from
+      // its own K and p whether its state fits it)
+      dense_smem = 0;
+      for (auto& j : jobs) {
+        int in_smem = 0;
+        const size_t need = dense_smem_bytes(j.dev.K, j.dev.p, j.dev.ld, &in_smem);
+        if (need > dense_smem_budget())
+          throw std::invalid_argument("dense x with p = " + std::to_string(j.dev.p) + " columns: a row ring of " +
+                                      std::to_string(need) + " bytes exceeds one SM's shared memory (" +
+                                      std::to_string(dense_smem_budget()) + "); this build handles dense p up to about 7000");
+        dense_smem = std::max(dense_smem, need);
+      }
       for (auto& j : jobs) {
         dense_kts |= static_cast<unsigned>(dense_kt_bucket(j.dev.K));
         dense_pens |= 1u << j.dev.penalty;
@@ -350,11 +358,11 @@ struct Engine {
     std::vector<FitDev> mirror(nf);
     for (int i = 0; i < nf; ++i) mirror[i] = jobs[i].dev;
     fits_dev = arena.upload(mirror);
-    prog_dev = arena.alloc<Progress>(nf);
+    prog_dev = arena.alloc<Progress>(nf, false);
     prog_host = arena.host<Progress>(nf);
     std::memset(prog_host, 0, sizeof(Progress) * nf);
     for (int i = 0; i < nf; ++i) prog_host[i].wscale = 1.0;
-    CK(cudaMemcpy(prog_dev, prog_host, sizeof(Progress) * nf, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(prog_dev, prog_host, sizeof(Progress) * nf, cudaMemcpyHostToDevice, stream));
     args_dev = arena.alloc<RoundArgs>(nf);
     args_host = arena.host<RoundArgs>(nf);
     seconds_setup = now_s() - t_begin;
@@ -371,8 +379,13 @@ struct Engine {
       j.pending_head = 0;
     }
     const size_t add = need - have;
+    // keep every mark from the newest one that is not ahead of the consumed position: settle_rng restarts from it
+    // (`consumed` only moves between rounds, after the helper threads have been joined)
+    size_t keep_from = 0;
+    for (size_t i = 0; i < j.marks.size(); ++i)
+      if (j.marks[i].first <= j.consumed) keep_from = i;
+    if (keep_from > 0) j.marks.erase(j.marks.begin(), j.marks.begin() + keep_from);
     j.marks.emplace_back(j.generated, *j.rng);
-    if (j.marks.size() > 8) j.marks.erase(j.marks.begin());
     const size_t old = j.pending.size();
     j.pending.resize(old + add);
     if (!draw_indices(j.rng, static_cast<uint32_t>(j.dev.n), static_cast<int64_t>(add), j.pending.data() + old)) return false;
@@ -436,6 +449,7 @@ struct Engine {
         return;
       }
     }
+    throw std::runtime_error("internal: no generator mark at or before the consumed position");
   }
 
   // ---------------------------------------------------------------------------------- rounds
@@ -617,6 +631,9 @@ int guarded(F&& body) {
     if (f.e != cudaSuccess) g_error = std::string(f.what) + ": " + cudaGetErrorString(f.e);
     else if (g_error.empty()) g_error = f.what;
     return (f.e == cudaSuccess) ? SGDNET_ERR_RNG : SGDNET_ERR_CUDA;
+  } catch (const std::invalid_argument& e) {
+    g_error = e.what();
+    return SGDNET_ERR_ARG;
   } catch (const std::bad_alloc&) {
     g_error = "host allocation failed";
     return SGDNET_ERR_ALLOC;
@@ -681,7 +698,10 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
       if (!xa.sparse) return s.control.n_classes == 1 ? 0 : 1;
       return (s.control.n_classes == 1 && !s.control.standardize) ? 2 : 3;
     };
-    int max_lambda = 0;      // row stride of `scores`: the caller sizes it from the controls it passed
+    // row stride of `scores`: the caller sizes it from the controls it passed. A fit's resolved path never has more
+    // than its own (or, with lambda_from, its source's) control.n_lambda values: FitPlan::build truncates a longer
+    // given sequence to n_lambda.
+    int max_lambda = 0;
     for (int i = 0; i < n_fits; ++i) max_lambda = std::max(max_lambda, specs[i].control.n_lambda);
     for (int v = 0; v < 4; ++v) {
       std::vector<int> group;
@@ -731,7 +751,7 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
           double* score_dev = eng.arena.alloc<double>(L);
           eng.predict_score(j.plan.family, j.plan.K, L, td, j.n_test, j.dev.a0_arch, j.dev.beta_arch, true, nullptr, score_dev);
           CK(cudaStreamSynchronize(eng.stream));
-          CK(cudaMemcpy(scores + size_t(group[g]) * max_lambda, score_dev, sizeof(double) * L, cudaMemcpyDeviceToHost));
+          CK(cudaMemcpy(scores + size_t(group[g]) * max_lambda, score_dev, sizeof(double) * std::min(L, max_lambda), cudaMemcpyDeviceToHost));
         }
       }
     }

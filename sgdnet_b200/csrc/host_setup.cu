@@ -497,6 +497,7 @@ std::string FitPlan::build(const HostDesign& d, std::vector<double> y, int Ky_, 
     }
   }
   if (static_cast<int>(lambda.size()) < n_lambda) return "lambda has fewer than n_lambda values";
+  lambda.resize(n_lambda);     // R sends nlambda = length(lambda) (R/sgdnet.R:242-245); extra values are never fitted
   double max_scale = y_scale[0];
   for (int k = 1; k < K; ++k) max_scale = std::max(max_scale, y_scale[k]);
   alpha.clear();

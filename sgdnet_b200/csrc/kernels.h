@@ -18,6 +18,7 @@ struct RoundArgs {
 
 // SAGA epochs, one CTA per fit (saga_dense.cu / saga_sparse.cu).
 size_t dense_smem_bytes(int K, int p, int ld, int* state_in_smem);
+size_t dense_smem_budget();
 cudaError_t launch_saga_dense(int n_fits, unsigned kts, unsigned pens, size_t smem, FitDev* fits, Progress* prog,
                               const RoundArgs* args, cudaStream_t st);
 int dense_kt_bucket(int K);   // 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for

@@ -60,8 +60,9 @@ size_t dense_smem_bytes(int K, int p, int ld, int* state_in_smem) {
     return fixed + state;
   }
   *state_in_smem = 0;
-  return fixed;
+  return fixed;     // may exceed the budget for very wide rows: the host refuses such a fit (engine.cu, finalize_batch)
 }
+size_t dense_smem_budget() { return 227 * 1024; }
 
 // KT: number of classes rounded up to 1 (K == 1: gaussian / binomial), 4, 8, 16 or 32; PEN: the penalty functor.
 // Both are compile-time so that the per-class loops unroll: the KT dot-product butterflies of a warp then run
@@ -89,10 +90,13 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
 
   int state_in_smem;
   {
-    // same decision as the host made when sizing dynamic shared memory
+    // W / g_sum live in shared memory when this fit's own layout fits the dynamic shared memory the host gave the
+    // launch (sized from the largest fit of the batch; fits of a batch may differ in K and p)
     size_t fixed = sizeof(double) * kRing * ld + sizeof(uint64_t) * kRing + sizeof(double) * 2 * nwarps * K + sizeof(double) * K;
     fixed = (fixed + 15) & ~size_t(15);
-    state_in_smem = (fixed + sizeof(double) * 2 * size_t(K) * p <= size_t(227 * 1024)) ? 1 : 0;
+    uint32_t dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    state_in_smem = (fixed + sizeof(double) * 2 * size_t(K) * p <= size_t(dyn_bytes)) ? 1 : 0;
   }
   DenseSmem sm = carve_dense(smem_raw, K, p, ld, nwarps, state_in_smem != 0);
   double* W = state_in_smem ? sm.W : f.W;
@@ -381,12 +385,8 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
 template <int KT, int PEN>
 static cudaError_t launch_dense_variant(int n_fits, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
                                         cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(saga_dense_kernel<KT, PEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(saga_dense_kernel<KT, PEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   saga_dense_kernel<KT, PEN><<<n_fits, kDenseThreads, smem, st>>>(fits, prog, args);
   return cudaGetLastError();
 }

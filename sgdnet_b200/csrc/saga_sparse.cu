@@ -1,21 +1,23 @@
 // saga_sparse.cu — sparse SAGA epochs with just-in-time lagged prox (reference: src/saga-sparse.h:76-155, 256-371).
 //
-// One persistent CTA per fit. Two kernels:
+// One persistent CTA per fit. Kernels:
 //
-//  saga_sparse_k1_kernel  K == 1 (gaussian / binomial), no virtual centring: the headline path (BASELINE configs
-//     2 and 5). Warp 0 is the solver: one lane per nonzero of the sampled row, the row's W / g_sum / lag entries are
-//     gathered once into registers, caught up (LaggedUpdate k = t), dotted with a warp-shuffle reduction, stepped,
-//     proxed (LaggedUpdate k = t+1, lag 1) and scattered back - each touched coefficient is read once and written
-//     once per update. Warp 1 is the producer: it walks the host-precomputed sample sequence ahead of the solver and
-//     stages each row's padded-CSR index/value runs plus y into a shared-memory ring with 1-D bulk copies
-//     (cp.async.bulk, complete_tx on an mbarrier per slot), so the solver never waits on HBM for row data.
-//     Coefficient state (W, g_sum, lag) is addressed in place: at these sizes (2 MB at p = 100k) it is L2-resident.
+//  saga_sparse_wave_kernel<S>  K == 1 (gaussian / binomial), no virtual centring: the headline path (BASELINE configs
+//     2 and 5). S worker warps take the sampled rows round-robin and overlap every update that shares no feature with
+//     a row still in flight; one chain warp runs the strictly serial scalar recurrence (intercept -> lp -> gradient);
+//     one producer warp streams each row's padded-CSR index / value runs (and, for rows that have conflicts, their
+//     conflict codes) into a shared-memory ring with 1-D bulk copies (cp.async.bulk, complete_tx on an mbarrier per
+//     slot). Coefficient state is one 32-byte record {w, g_sum, lag} per feature, L2-resident, read and written
+//     once per nonzero per update with 256-bit accesses. The exactness argument is in the comment block below.
 //     Algorithmic HBM bytes per update: 12*nnz_row + 16 (row info) + 4 (index) + 8 (y) + 16 (gradient memory).
+//
+//  wave_deps_kernel  which features of a row are also held by one of the S-1 rows before it, from the host-drawn
+//     sampling sequence alone (so it can run ahead of the solver).
 //
 //  saga_sparse_generic_kernel  any K <= 32 and/or standardize = TRUE (the reference's O(p*K) virtual-centring sweeps,
 //     src/saga-sparse.h:127-128, 276-277, reproduced as block-wide passes). Phases are separated by block barriers.
 //
-// Epoch end (both): Reset(n) over all features by the whole CTA, W *= wscale, lag = 0, convergence test
+// Epoch end (all): Reset(n) over all features by the whole CTA, W *= wscale, lag = 0, convergence test
 // (src/saga-sparse.h:340-348, 367; src/utils.h:240-262).
 #include <algorithm>
 #include <cstddef>
@@ -120,7 +122,7 @@ struct WaveSlotMeta {
   int64_t start;
   double y;
   uint32_t dup;     // distance to the most recent in-window row with the same sample (0 = none)
-  uint32_t pad_;
+  uint32_t has_code;   // the row shares a feature with a row of its window: its conflict codes were copied
 };
 
 struct __align__(128) WaveSmem {
@@ -285,8 +287,12 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
           if (lo < nnz2 && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
         }
       }
-      ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
-      if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd);
+      // most rows share nothing with their window (82 % at config 2's density): their 256 B of codes are neither
+      // written here nor copied by the solver's producer; bit 7 of dup[] says which rows have codes
+      const bool any = __any_sync(0xffffffffu, (ent[0] | ent[1] | ent[2] | ent[3]) != 0u);
+      if (any)
+        ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
+      if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd | (any ? 0x80u : 0u));
     }
   }
 }
@@ -381,16 +387,17 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
         m.nnz = ri.nnz;
         m.start = ri.start;
         m.y = y;
-        m.dup = dv;
-        m.pad_ = 0;
+        m.dup = dv & 0x7fu;
+        m.has_code = dv >> 7;
         sm.meta[lane] = m;
         if (ri.nnz > 0 && ri.nnz <= kCap) {
           const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
           const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
-          mbar_expect_tx(&sm.full[lane], bi + bv + 256u);
+          const uint32_t bc = m.has_code ? 256u : 0u;
+          mbar_expect_tx(&sm.full[lane], bi + bv + bc);
           bulk_g2s(sm.idx[lane], f.ci + ri.start, bi, &sm.full[lane]);
           bulk_g2s(sm.val[lane], f.cv + ri.start, bv, &sm.full[lane]);
-          bulk_g2s(sm.code[lane], edep + size_t(t) * 32, 256u, &sm.full[lane]);
+          if (bc) bulk_g2s(sm.code[lane], edep + size_t(t) * 32, 256u, &sm.full[lane]);
         } else {
           mbar_arrive(&sm.full[lane]);
         }
@@ -536,7 +543,8 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       bool valid[kChunks];
       double vr[kChunks], wr[kChunks], gr[kChunks];
       uint32_t lr[kChunks], dr[kChunks];   // dr: conflict entry (distance | position << 4 | kCodeGlobal)
-      const uint64_t code = sm.code[slot][lane];
+      const uint64_t code_raw = sm.code[slot][lane];
+      const uint64_t code = m.has_code ? code_raw : 0ull;   // stale ring contents when the row has no codes
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int e = c * 32 + lane;
@@ -648,8 +656,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
           cnt += hit ? 1 : 0;
           c1 = hit ? c : c1;
         }
-        const bool fm_ok = true;
-        if (fm_ok && __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt)) == 1u) {
+        if (__reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt)) == 1u) {
           const bool late_lane = cnt == 1;
           for (uint32_t rest = need_g & ~(1u << dnear); rest != 0;) {     // older rows: complete already
             const uint32_t d = 31u - static_cast<uint32_t>(__clz(rest));
@@ -1210,13 +1217,10 @@ int wave_warps() {
 
 template <int S>
 static cudaError_t launch_wave(int n_fits, FitDev* fits, Progress* prog, const RoundArgs* args, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(saga_sparse_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(WaveSmem)));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // per device and cheap: set on every launch (the ABI lets one process move between devices, sgdnet_set_device)
+  cudaError_t e = cudaFuncSetAttribute(saga_sparse_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(sizeof(WaveSmem)));
+  if (e != cudaSuccess) return e;
   saga_sparse_wave_kernel<S><<<n_fits, wave_block_warps(S) * 32, sizeof(WaveSmem), st>>>(fits, prog, args);
   return cudaGetLastError();
 }
@@ -1228,12 +1232,8 @@ cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* pro
   dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min(want, cap))), n_fits);
   const int window = wave_warps() - 1;
   const size_t smem = size_t(kDepRows + window) * ((kCap + kDepBitWords) * 4 + 8);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) return e;
   wave_deps_kernel<<<grid, 256, smem, st>>>(fits, prog, args, window);
   return cudaGetLastError();
 }

@@ -39,12 +39,30 @@ def inputs():
         "c2mini": synth.binomial_sparse(1500, 300, 16, seed=1002),
         "sparse_gaussian": synth.random_data(200, 8, "gaussian", True, density=0.3, seed=5),
         "c3mini": synth.multinomial_dense(400, 30, 4, seed=1003),
-        "c4mini": synth.mgaussian_dense(300, 40, 3, seed=1004),
+        # (seed 1: with seed 1004 the reference build and the arithmetic specification of include/sgdnet_arith.h part
+        # ways at the first lambda - 91 vs 94 epochs, a dense dot product associated differently moves the convergence
+        # ratio across the threshold - and nothing of that path is comparable; see tests/ref_vectors.py)
+        "c4mini": synth.mgaussian_dense(300, 40, 3, seed=1),
         "sparse_multinomial": synth.random_data(150, 6, "multinomial", True, density=0.5, seed=8),
     }
 
 
 BUNDLED = ("abalone", "heart", "wine", "student")   # already fixtures of their own; not stored twice
+
+# Inputs too large to commit: regenerated from their seed wherever the vectors are used (numpy's PCG64 streams are
+# stable); a checksum of the generated arrays is stored with the outputs and checked on load.
+GENERATED = {
+    # sparse + standardize = TRUE on genuinely sparse rows (16 of 2000 columns): the reference's O(p) virtual-centring
+    # sweeps interleaved with the lagged updates (src/saga-sparse.h:127-128, 276-277)
+    "c2std": lambda: synth.binomial_sparse(20000, 2000, 16, seed=1012),
+}
+
+
+def checksum(x, y):
+    x = sp.csc_matrix(x)
+    x.sort_indices()
+    return np.array([float(x.data.sum()), float(np.dot(x.data, np.arange(x.data.size) % 97)), float(x.indices.sum()),
+                     float(np.asarray(y, dtype=np.float64).sum())])
 
 CASES = {
     # BASELINE config 1 exactly (R defaults: standardize, intercept, thresh 1e-3, maxit 1000, set.seed(1))
@@ -75,6 +93,7 @@ CASES = {
     "fixed_c3mini_dense_multinomial": ("c3mini", dict(family="multinomial", alpha=0.8, nlambda=8, thresh=0.0, maxit=5, seed=1)),
     "fixed_c4mini_dense_mgaussian": ("c4mini", dict(family="mgaussian", alpha=1.0, nlambda=8, thresh=0.0, maxit=5, seed=1)),
     "fixed_sparse_multinomial_std": ("sparse_multinomial", dict(family="multinomial", alpha=0.5, standardize=True, nlambda=6, thresh=0.0, maxit=5, seed=9)),
+    "fixed_c2std_sparse_binomial_enet_std": ("c2std", dict(family="binomial", alpha=0.5, standardize=True, nlambda=5, thresh=0.0, maxit=8, seed=1)),
     "fixed_sparse_gaussian_std_nointercept": ("sparse_gaussian", dict(family="gaussian", alpha=0.3, standardize=True, intercept=False, nlambda=6, thresh=0.0, maxit=5, seed=2)),
 }
 
@@ -83,8 +102,11 @@ def main():
     ref = Library(REF_SO, "ref_")
     store = {}
     ins = inputs()
+    for key, gen in GENERATED.items():
+        ins[key] = gen()
+        store[f"in/{key}/checksum"] = checksum(*ins[key])
     for key, (x, y) in ins.items():
-        if key in BUNDLED:
+        if key in BUNDLED or key in GENERATED:
             continue
         if sp.issparse(x):
             x = sp.csc_matrix(x)

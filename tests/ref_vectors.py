@@ -9,7 +9,7 @@ import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-from make_ref_vectors import BUNDLED, CASES  # noqa: E402  (names and kwargs only; nothing is computed on import)
+from make_ref_vectors import BUNDLED, CASES, GENERATED, checksum  # noqa: E402  (names and kwargs only; nothing is computed on import)
 
 _NPZ = None
 
@@ -21,7 +21,17 @@ def _npz():
     return _NPZ
 
 
+_GEN_CACHE = {}
+
+
 def case_input(key):
+    if key in GENERATED:
+        if key not in _GEN_CACHE:
+            x, y = GENERATED[key]()
+            np.testing.assert_array_equal(checksum(x, y), _npz()[f"in/{key}/checksum"],
+                                          err_msg=f"generated input '{key}' is not the one the reference vectors were made from")
+            _GEN_CACHE[key] = (x, y)
+        return _GEN_CACHE[key]
     if key in BUNDLED:
         d = np.load(os.path.join(ROOT, "tests", "golden", key + ".npz"))
         pre = ""

@@ -35,6 +35,41 @@ def test_config2_sparse_binomial_lasso_1m_x_100k(cuda, oracle):
     assert_fit_parity(g.raw, r.raw)
 
 
+def test_config2_full_100_lambda_path_matches_the_reference_build(cuda):
+    """BASELINE config 2 END TO END through the plugin call sgdnet_fit_sparse (host CSC in, archives out): the whole
+    100-lambda path against what the reference's own compiled code produced on the same inputs and seed
+    (tests/golden/c2_full_path_ref.json; 2302 s on one CPU core): lambda path exact, 381 epochs lambda by lambda,
+    the same number of nonzero coefficients at every lambda, deviances within 1e-6 relative. Also BASELINE metric (ii),
+    the lambda-path fit time, written to gpurun_out/c2_full_path_gpu.json."""
+    import json
+    import os
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "c2_full_path_ref.json")) as fh:
+        ref = json.load(fh)
+    x, y = synth.binomial_sparse(1_000_000, 100_000, 100, seed=1002)
+    t0 = time.perf_counter()
+    g = sg.sgdnet(x, y, family="binomial", alpha=1.0, standardize=False, intercept=True, nlambda=100, thresh=1e-3,
+                  maxit=1000, seed=1, backend=cuda)
+    wall = time.perf_counter() - t0
+    np.testing.assert_array_equal(g.raw.lambda_, np.array(ref["lambda"]), err_msg="lambda path")
+    np.testing.assert_array_equal(g.raw.epochs, np.array(ref["epochs_per_lambda"]), err_msg="epochs per lambda")
+    assert g.npasses == ref["npasses"] == 381
+    assert not g.raw.return_codes.any()
+    nnz = [int(np.count_nonzero(g.raw.beta[l])) for l in range(100)]
+    assert nnz == ref["nonzeros_per_lambda"], "number of nonzero coefficients per lambda"
+    dev_g, dev_r = 1.0 - g.raw.dev_ratio, 1.0 - np.array(ref["dev_ratio"])
+    assert np.max(np.abs(dev_g - dev_r)) <= 1e-6 * np.max(np.abs(dev_r))
+    out = {"workload": ref["what"], "call": "sgdnet_fit_sparse (host buffers)", "wall_s": wall, "npasses": int(g.npasses),
+           "updates_per_s": 1_000_000 * int(g.npasses) / wall, "seconds_setup": g.raw.seconds_setup,
+           "seconds_solver": g.raw.seconds_solver, "seconds_deviance": g.raw.seconds_deviance,
+           "kernel_launches": int(g.raw.kernel_launches),
+           "max_rel_deviance_diff_vs_reference_build": float(np.max(np.abs(dev_g - dev_r)) / np.max(np.abs(dev_r)))}
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "c2_full_path_gpu.json"), "w") as fh:
+        json.dump(out, fh)
+
+
 def test_config5_shape_cv_folds_500k_x_50k(cuda, oracle):
     """One alpha of the 10-fold grid at config 5's size: 10 fold fits (50k rows each) + the full fit in one batch;
     two of the fold fits and their held-out deviances are checked against the oracle."""

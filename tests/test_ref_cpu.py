@@ -52,8 +52,13 @@ def test_oracle_portable_matches_reference_vectors(oracle, name):
     x, y, kw, exp = case(name)
     assert oracle.lib.oracle_get_arith() == 1
     n_cmp = assert_matches_reference(sg.sgdnet(x, y, backend=oracle, **kw).raw, exp, exact=False)
-    if name.startswith("fixed_"):
-        assert n_cmp == len(exp["lambda_"])     # fixed path lengths: the whole path is comparable
+    # Every committed case is comparable over its WHOLE path: the fixed-length ones by construction, the converging
+    # ones because their epoch counts agree lambda by lambda. That is a property of these inputs, not a guarantee: the
+    # arithmetic specification associates dense reductions differently from the reference build's sequential sums (as
+    # a real Eigen build would), and a convergence ratio that lands within an ulp-level distance of `thresh` can move
+    # an epoch count (mgaussian 300 x 40 with data seed 1004 does: 94 vs 91 epochs at the first lambda). A case that
+    # stops comparing is a regression to look at, so the count is asserted rather than tolerated.
+    assert n_cmp == len(exp["lambda_"])
 
 
 def test_c1_path_length_is_the_reference_builds(oracle):
