@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SGDNET_ABI_VERSION 2
+#define SGDNET_ABI_VERSION 3
 
 /* status codes */
 #define SGDNET_OK            0
@@ -89,6 +89,14 @@ typedef struct sgdnet_rng {
 void   sgdnet_rng_set_seed(sgdnet_rng* rng, uint32_t seed);
 /* One R `unif_rand()` draw from an SGDNET_RNG_MT state (MT19937 genrand * 2^-32, with R's fixup). */
 double sgdnet_rng_unif(sgdnet_rng* rng);
+/*
+ * The sampling sequence of `n_epochs` epochs over n samples, floor(runif(0, n)) per update, as the solver's launches
+ * consume it. With SGDNET_RNG_MT the library generates it ON THE DEVICE (block-parallel MT19937 regeneration), so no
+ * index ever crosses PCIe; this entry point exposes that generator for verification: seq receives n * n_epochs
+ * indices, states (may be NULL) n_epochs + 1 generator states, states[e] = the generator after e epochs, and *rng is
+ * left advanced by n * n_epochs draws. on_host != 0 runs the same regeneration schedule on the CPU (no device needed).
+ */
+int    sgdnet_rng_indices(sgdnet_rng* rng, uint32_t n, int32_t n_epochs, uint32_t* seq, sgdnet_rng* states, int32_t on_host);
 
 /*
  * The list returned at src/sgdnet.cpp:275-284. Buffers are allocated by the library and released

@@ -240,6 +240,9 @@ class Library:
             f.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]; f.restype = C.c_int
             f = self.sym("session_result"); f.argtypes = [C.c_void_p, C.POINTER(Result)]; f.restype = C.c_int
             f = self.sym("session_destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+        if self.has("rng_indices"):
+            f = self.sym("rng_indices")
+            f.argtypes = [C.POINTER(Rng), C.c_uint32, C.c_int32, c_uint32_p, C.POINTER(Rng), C.c_int32]; f.restype = C.c_int
         if self.has("set_device"):
             f = self.sym("set_device"); f.argtypes = [C.c_int]; f.restype = C.c_int
             f = self.sym("device_count"); f.argtypes = [C.POINTER(C.c_int)]; f.restype = C.c_int
@@ -269,6 +272,14 @@ class Library:
     def unif(self, rng: Rng, count: int) -> np.ndarray:
         f = self.sym("rng_unif")
         return np.array([f(C.byref(rng)) for _ in range(count)])
+
+    def rng_indices(self, rng: Rng, n: int, n_epochs: int, on_host: bool = False):
+        """(indices [n_epochs * n], list of n_epochs + 1 generator states); `rng` is advanced in place."""
+        seq = np.empty(n * n_epochs, dtype=np.uint32)
+        states = (Rng * (n_epochs + 1))()
+        self.check(self.sym("rng_indices")(C.byref(rng), C.c_uint32(n), C.c_int32(n_epochs), _ptr(seq, c_uint32_p), states,
+                                           C.c_int32(1 if on_host else 0)), "rng_indices")
+        return seq, states
 
     # -- fits ---------------------------------------------------------------------------------
     @staticmethod

@@ -43,6 +43,7 @@ struct __align__(32) FeatState {
 
 // Everything one fit needs on the device. One of these per fit lives in HBM; CTA `blockIdx.x` (or blockIdx.y for
 // the grid-wide passes) works on fit `blockIdx.x`. The host mirrors the struct and re-reads only `Progress`.
+struct Progress;
 struct FitDev {
   // ---- problem shape
   int32_t sparse, family, penalty, fit_intercept;
@@ -78,6 +79,7 @@ struct FitDev {
   double *partials;          // per-block partial sums for the grid-wide passes
   int32_t debug;
   int32_t pad0_;             // always 0 (read as a run-time zero, see dep_on)
+  struct Progress* mirror;   // pinned host copy of the fit's Progress, written by the kernels that change it
 };
 
 // Device-updated progress of one fit; read back by the host after every round.
@@ -87,9 +89,25 @@ struct Progress {
   uint32_t it_outer;         // epochs run so far at lambda_ind
   uint32_t npasses;          // accumulated over the path
   uint32_t epochs_last_launch;
-  uint32_t pad_;
+  uint32_t round_seen;       // id of the last round (RoundArgs::round_id) whose result this is; the host polls it
   double   wscale;           // carried only inside an epoch; 1.0 between epochs
 };
+
+// The host does not synchronise streams to learn that a round is over: the one thread that updates a fit's Progress
+// copies it to pinned host memory, payload first, then (system-scope fence in between) the round id the host is
+// polling for. Stream order still governs everything on the device.
+__device__ __forceinline__ void publish_progress(Progress* mirror, const Progress& pg, uint32_t round_id) {
+  if (mirror == nullptr) return;
+  volatile Progress* m = mirror;
+  m->lambda_ind = pg.lambda_ind;
+  m->status = pg.status;
+  m->it_outer = pg.it_outer;
+  m->npasses = pg.npasses;
+  m->epochs_last_launch = pg.epochs_last_launch;
+  m->wscale = pg.wscale;
+  __threadfence_system();
+  m->round_seen = round_id;
+}
 
 // ------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ double warp_sum(double v) {

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -31,6 +32,14 @@
 namespace sgd {
 
 thread_local std::string g_error;
+
+// Every fit of a batch runs on its own stream. The driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues
+// (8 by default, 32 at most); streams that share a queue can hold each other up. Ask for the maximum unless the
+// caller chose a value (only effective when the CUDA context is created after this library is loaded; harnesses that
+// initialise CUDA first set the variable themselves).
+struct ConnectionsEnv {
+  ConnectionsEnv() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_env;
 
 struct CudaFail {
   cudaError_t e;
@@ -130,30 +139,67 @@ struct DeviceDesign {
   const double *c = nullptr, *x_center = nullptr, *x_scale = nullptr;
 };
 
+enum class Variant { Dense, SparseK1, SparseGeneric };
+enum class Phase { Idle, Solver, Finish, Parked, Done };
+
+// One fit of a batch = one asynchronous pipeline: its own stream, its own rounds
+//     [sampling indices -> conflict codes] -> lag-scaling table (new lambda) -> SAGA epochs
+//     and, when a lambda is finished (or after every epoch in debug mode), [epoch loss] -> deviance + rescale + archive
+// submitted as soon as the fit's previous launch has published its Progress to pinned host memory. Nothing makes a
+// small fit wait for a large one.
 struct FitJob {
   std::shared_ptr<HostDesign> design;
   DeviceDesign ddev;
   FitPlan plan;
   sgdnet_rng* rng = nullptr;
-  FitDev dev{};                       // host mirror
-  // index stream
+  FitDev dev{};                       // host mirror of the device struct
+  FitDev* dev_ptr = nullptr;
+  Progress* prog_ptr = nullptr;
+  Progress* mirror = nullptr;         // pinned: written by the kernels (publish_progress), polled by the host
+  Variant variant = Variant::Dense;
+  // ---- index stream, host generators (callback / explicit sequence / MT when SGDNET_HOST_RNG is set)
   std::vector<uint32_t> pending;      // generated, not yet consumed
   size_t pending_head = 0;
   uint64_t consumed = 0;              // draws consumed by finished epochs
   std::vector<std::pair<uint64_t, sgdnet_rng>> marks;   // (draws generated before, generator state) per block
   uint64_t generated = 0;
-  uint32_t* seq_dev = nullptr;
   uint32_t* seq_pin = nullptr;
-  uint64_t* dep_dev = nullptr;        // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
-  uint8_t* dup_dev = nullptr;
+  // ---- index stream, device generator (R's Mersenne-Twister, rng.cu)
+  bool device_rng = false;
+  MtState* rng_dev = nullptr;         // the caller's generator as uploaded at the start of run()
+  MtState* rng_pin = nullptr;
+  const MtState* cur_state = nullptr; // generator state the next launch starts from (device)
+  sgdnet_rng handed_back{};           // the generator as last returned to the caller (its prepared launch stays valid)
+  bool have_handed_back = false;
+  // ---- launch buffers, double buffered: [buf] is consumed by the launch in flight while [buf ^ 1] is prepared
+  uint32_t* seq_dev[2] = {nullptr, nullptr};
+  uint64_t* dep_dev[2] = {nullptr, nullptr};   // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
+  uint8_t* dup_dev[2] = {nullptr, nullptr};
+  MtState* snap_dev[2] = {nullptr, nullptr};   // [epochs_per_launch + 1] generator snapshots at epoch boundaries
   int epochs_per_launch = 1;
-  bool done = false;
-  // scoring of held-out rows after the fit (cv)
+  int buf = 0;
+  bool prepped = false;               // [buf] already holds the indices (+ codes) that start at cur_state
+  bool prepped_next = false;          // [buf ^ 1] is being prepared on st_prep assuming this launch uses all its epochs
+  // ---- pipeline
+  cudaStream_t st = nullptr, st_prep = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_idx = nullptr, ev_prep = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+  Phase phase = Phase::Idle;
+  uint32_t round_id = 0;
+  int ne_submitted = 0;
+  bool idx_on_prep = false;           // this launch's indices were produced on st_prep
+  bool needs_finish = false;          // the last solver launch ended a lambda (or, debug mode, an epoch): passes are due
+  bool stale_prep = false;            // a prepared launch was discarded; its kernels may still be running on st_prep
+  int loss_blocks = 1;
+  size_t dense_smem = 0;
+  double seconds_solver = 0.0, seconds_dev = 0.0;
+  uint64_t launches = 0;
+  // ---- scoring of held-out rows after the fit (cv)
   const int32_t* test_rows = nullptr;
   int64_t n_test = 0;
+  int32_t measure = 0;
+  double* score_dev = nullptr;
+  bool scored = false;
 };
-
-enum class Variant { Dense, SparseK1, SparseGeneric };
 
 struct Engine {
   Arena arena;
@@ -162,28 +208,18 @@ struct Engine {
   int Ky = 1;
   std::map<std::pair<const int32_t*, int>, std::pair<std::shared_ptr<HostDesign>, DeviceDesign>> designs;
   std::vector<FitJob> jobs;
-  FitDev* fits_dev = nullptr;
-  Progress* prog_dev = nullptr;
-  Progress* prog_host = nullptr;      // pinned
-  RoundArgs* args_dev = nullptr;
-  RoundArgs* args_host = nullptr;     // pinned
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  int loss_blocks = 1;
+  cudaStream_t stream = nullptr;      // setup / scoring of single calls
   int sms = 148;
-  int64_t max_rows_per_launch = 1;
-  bool trace_rounds = std::getenv("SGDNET_TRACE_ROUNDS") != nullptr;   // per-round device times on stderr
-  size_t dense_smem = 0;
-  unsigned dense_kts = 0, dense_pens = 0;   // class-count buckets / penalties present (dense kernel instantiations)
-  Variant variant = Variant::Dense;
-  bool any_debug = false;
-  uint64_t launches = 0;
-  double seconds_solver = 0.0, seconds_dev = 0.0, seconds_setup = 0.0;
+  bool trace_rounds = std::getenv("SGDNET_TRACE_ROUNDS") != nullptr;   // per-launch device times on stderr
+  bool host_rng = std::getenv("SGDNET_HOST_RNG") != nullptr;           // draw MT indices on the host (development aid)
+  bool no_overlap = std::getenv("SGDNET_NO_PREP_OVERLAP") != nullptr;  // prepare a launch only when it is due
+  double seconds_setup = 0.0;
   double t_begin = 0.0;
   // raw design for scoring (device)
   DeviceDesign raw_dev;
   bool raw_uploaded = false;
   double* yraw_dev = nullptr;
+  std::map<const int32_t*, int32_t*> test_dev;
 
   Engine() {
     int count = 0;
@@ -191,15 +227,18 @@ struct Engine {
     if (e != cudaSuccess || count == 0) throw CudaFail{e == cudaSuccess ? cudaErrorNoDevice : e, "no CUDA device (no CPU fallback)"};
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     arena.stream = stream;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
-    CK(cudaEventCreate(&ev2));
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     t_begin = now_s();
   }
   ~Engine() {
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (ev2) cudaEventDestroy(ev2);
+    for (FitJob& j : jobs) {
+      for (cudaEvent_t ev : {j.ev0, j.ev1, j.ev_idx, j.ev_prep, j.ev_f0, j.ev_f1})
+        if (ev) cudaEventDestroy(ev);
+      if (j.st) cudaStreamDestroy(j.st);
+      if (j.st_prep) cudaStreamDestroy(j.st_prep);
+    }
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -229,8 +268,10 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------------------------- one fit
-  std::string add_fit(const int32_t* rows, int64_t n_rows, const sgdnet_control& ctl, sgdnet_rng* rng,
-                      const int32_t* test_rows, int64_t n_test) {
+  // Step 1 (serial): the design. Step 2 (may run on a helper thread, touches only the job): the plan. Step 3 (serial):
+  // device state.
+  std::string add_fit_design(const int32_t* rows, int64_t n_rows, const sgdnet_control& ctl, sgdnet_rng* rng,
+                             const int32_t* test_rows, int64_t n_test, int32_t measure) {
     if (ctl.n_lambda <= 0) return "n_lambda must be positive";
     if (!rng) return "rng is null";
     if (rows)
@@ -240,20 +281,25 @@ struct Engine {
     auto dsn = get_design(rows, n_rows, ctl.standardize != 0);
     job.design = dsn.first;
     job.ddev = dsn.second;
-    const HostDesign& d = *job.design;
-    // response restricted to the fit's rows
-    std::vector<double> ysub(static_cast<size_t>(d.n) * Ky);
-    for (int k = 0; k < Ky; ++k)
-      for (int64_t i = 0; i < d.n; ++i)
-        ysub[static_cast<size_t>(k) * d.n + i] = y_cm[static_cast<size_t>(k) * raw.n + (rows ? rows[i] : i)];
-    PhaseTimer pt;
-    std::string err = job.plan.build(d, std::move(ysub), Ky, ctl);
-    if (!err.empty()) return err;
-    pt.lap("plan (lambda path, steps)");
     job.rng = rng;
     job.test_rows = test_rows;
     job.n_test = n_test;
+    job.measure = measure;
+    jobs.push_back(std::move(job));
+    return "";
+  }
 
+  std::string build_plan(FitJob& job, const int32_t* rows, const sgdnet_control& ctl) {
+    const HostDesign& d = *job.design;
+    std::vector<double> ysub(static_cast<size_t>(d.n) * Ky);     // response restricted to the fit's rows
+    for (int k = 0; k < Ky; ++k)
+      for (int64_t i = 0; i < d.n; ++i)
+        ysub[static_cast<size_t>(k) * d.n + i] = y_cm[static_cast<size_t>(k) * raw.n + (rows ? rows[i] : i)];
+    return job.plan.build(d, std::move(ysub), Ky, ctl);
+  }
+
+  void alloc_fit(FitJob& job) {
+    const HostDesign& d = *job.design;
     const FitPlan& pl = job.plan;
     const int K = pl.K, p = d.p, L = pl.n_lambda;
     FitDev& f = job.dev;
@@ -280,7 +326,8 @@ struct Engine {
     f.gsi = arena.alloc<double>(K);
     f.gmem = arena.alloc<double>(size_t(d.n) * K);
     f.lag = arena.alloc<uint32_t>(p);
-    f.st = (d.sparse && K == 1 && !f.standardize) ? arena.alloc<FeatState>(p) : nullptr;
+    job.variant = !d.sparse ? Variant::Dense : ((K == 1 && !f.standardize) ? Variant::SparseK1 : Variant::SparseGeneric);
+    f.st = (job.variant == Variant::SparseK1) ? arena.alloc<FeatState>(p) : nullptr;
     f.lag_scaling = d.sparse ? arena.alloc<double>(size_t(d.n) + 1, false) : nullptr;
     f.gamma = arena.upload(pl.gamma);
     f.alpha = arena.upload(pl.alpha);
@@ -300,77 +347,77 @@ struct Engine {
     f.codes = arena.alloc<uint32_t>(L);
     f.debug = pl.debug ? 1 : 0;
     f.losses = pl.debug ? arena.alloc<double>(size_t(L) * pl.max_iter) : nullptr;
-    any_debug = any_debug || pl.debug;
 
-    // epochs per launch: amortise the round trip for small problems; the callback generator and the debug loss need
-    // a host visit after every epoch
+    // epochs per launch: amortise the host visit for small problems; the callback generator and the debug loss need
+    // one after every epoch
     int epl = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(16, 200000 / std::max<int64_t>(1, d.n))));
     if (const char* env = std::getenv("SGDNET_EPOCHS_PER_LAUNCH")) epl = std::max(1, std::atoi(env));   // tuning knob
-    if (pl.debug || rng->kind == SGDNET_RNG_CALLBACK) epl = 1;
+    if (pl.debug || job.rng->kind == SGDNET_RNG_CALLBACK) epl = 1;
     epl = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(epl), std::max<uint32_t>(1u, pl.max_iter)));
     job.epochs_per_launch = epl;
-    job.seq_dev = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
-    job.seq_pin = arena.host<uint32_t>(size_t(epl) * d.n);
-    if (d.sparse && K == 1 && !f.standardize) {
-      job.dep_dev = arena.alloc<uint64_t>(size_t(epl) * d.n * 32, false);
-      job.dup_dev = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
+    job.device_rng = job.rng->kind == SGDNET_RNG_MT && !host_rng;
+    const int nbuf = job.device_rng ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+      job.seq_dev[b] = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
+      if (job.variant == Variant::SparseK1) {
+        job.dep_dev[b] = arena.alloc<uint64_t>(size_t(epl) * d.n * 32, false);
+        job.dup_dev[b] = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
+      }
+      if (job.device_rng) job.snap_dev[b] = arena.alloc<MtState>(size_t(epl) + 1, false);
     }
-    jobs.push_back(std::move(job));
+    if (job.device_rng) {
+      job.rng_dev = arena.alloc<MtState>(1, false);
+      job.rng_pin = arena.host<MtState>(1);
+    } else {
+      job.seq_pin = arena.host<uint32_t>(size_t(epl) * d.n);
+    }
+    // streaming passes: enough CTAs to fill the GPU when the fit's pass runs alone
+    job.loss_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(int64_t(sms) * 4, (d.n + 7) / 8)));
+    f.partials = arena.alloc<double>(job.loss_blocks);
+    if (job.variant == Variant::Dense) {
+      int in_smem = 0;
+      job.dense_smem = dense_smem_bytes(K, p, d.ld, &in_smem);
+      if (job.dense_smem > dense_smem_budget())
+        throw std::invalid_argument("dense x with p = " + std::to_string(p) + " columns: a row ring of " +
+                                    std::to_string(job.dense_smem) + " bytes exceeds one SM's shared memory (" +
+                                    std::to_string(dense_smem_budget()) + "); this build handles dense p up to about 7000");
+    }
+    job.mirror = arena.host<Progress>(1);
+    std::memset(job.mirror, 0, sizeof(Progress));
+    job.mirror->wscale = 1.0;
+    f.mirror = job.mirror;
+    job.dev_ptr = arena.upload_from(&job.dev, 1);
+    job.prog_ptr = arena.upload_from(job.mirror, 1);
+    CK(cudaStreamCreateWithFlags(&job.st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&job.st_prep, cudaStreamNonBlocking));
+    for (cudaEvent_t* ev : {&job.ev0, &job.ev1, &job.ev_f0, &job.ev_f1}) CK(cudaEventCreate(ev));
+    for (cudaEvent_t* ev : {&job.ev_idx, &job.ev_prep}) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  }
+
+  // add_fit_design + build_plan + alloc_fit for one fit (single-fit entry points)
+  std::string add_fit(const int32_t* rows, int64_t n_rows, const sgdnet_control& ctl, sgdnet_rng* rng,
+                      const int32_t* test_rows, int64_t n_test) {
+    std::string err = add_fit_design(rows, n_rows, ctl, rng, test_rows, n_test, 0);
+    if (!err.empty()) return err;
+    PhaseTimer pt;
+    err = build_plan(jobs.back(), rows, ctl);
+    if (!err.empty()) {
+      jobs.pop_back();
+      return err;
+    }
+    pt.lap("plan (lambda path, steps)");
+    alloc_fit(jobs.back());
     pt.lap("state alloc + upload");
     return "";
   }
 
   void finalize_batch() {
-    const int nf = static_cast<int>(jobs.size());
-    // one kernel variant per batch
-    const FitJob& j0 = jobs[0];
-    if (!j0.dev.sparse) variant = Variant::Dense;
-    else variant = (j0.dev.K == 1 && !j0.dev.standardize) ? Variant::SparseK1 : Variant::SparseGeneric;
-    int64_t max_n = 0;
-    for (auto& j : jobs) max_n = std::max(max_n, j.dev.n);
-    if (variant == Variant::Dense) {
-      // the launch's dynamic shared memory: what the most demanding fit of the batch needs (each CTA decides from
-      // its own K and p whether its state fits it)
-      dense_smem = 0;
-      for (auto& j : jobs) {
-        int in_smem = 0;
-        const size_t need = dense_smem_bytes(j.dev.K, j.dev.p, j.dev.ld, &in_smem);
-        if (need > dense_smem_budget())
-          throw std::invalid_argument("dense x with p = " + std::to_string(j.dev.p) + " columns: a row ring of " +
-                                      std::to_string(need) + " bytes exceeds one SM's shared memory (" +
-                                      std::to_string(dense_smem_budget()) + "); this build handles dense p up to about 7000");
-        dense_smem = std::max(dense_smem, need);
-      }
-      for (auto& j : jobs) {
-        dense_kts |= static_cast<unsigned>(dense_kt_bucket(j.dev.K));
-        dense_pens |= 1u << j.dev.penalty;
-      }
-    }
-    // streaming passes: enough CTAs to fill the GPU across the fits of the batch, at least one per fit
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-    for (auto& j : jobs) max_rows_per_launch = std::max<int64_t>(max_rows_per_launch, j.dev.n * j.epochs_per_launch);
-    const int64_t want = std::max<int64_t>(1, (int64_t(sms) * 4 + nf - 1) / nf);
-    loss_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (max_n + 7) / 8)));
-    for (auto& j : jobs) j.dev.partials = arena.alloc<double>(loss_blocks);
-
-    std::vector<FitDev> mirror(nf);
-    for (int i = 0; i < nf; ++i) mirror[i] = jobs[i].dev;
-    fits_dev = arena.upload(mirror);
-    prog_dev = arena.alloc<Progress>(nf, false);
-    prog_host = arena.host<Progress>(nf);
-    std::memset(prog_host, 0, sizeof(Progress) * nf);
-    for (int i = 0; i < nf; ++i) prog_host[i].wscale = 1.0;
-    CK(cudaMemcpyAsync(prog_dev, prog_host, sizeof(Progress) * nf, cudaMemcpyHostToDevice, stream));
-    args_dev = arena.alloc<RoundArgs>(nf);
-    args_host = arena.host<RoundArgs>(nf);
+    CK(cudaStreamSynchronize(stream));     // zero fills of the state (ordered on `stream`) precede every fit's stream
     seconds_setup = now_s() - t_begin;
   }
 
-  // ---------------------------------------------------------------------------------- index stream
-  // Makes sure `need` undrawn-by-the-device indices are pending (host memory). May run on a helper thread while the
-  // device works: it touches only this job's generator and buffers.
+  // ---------------------------------------------------------------------------------- index stream (host generators)
+  // Makes sure `need` undrawn-by-the-device indices are pending (host memory).
   bool ensure_pending(FitJob& j, size_t need) {
     size_t have = j.pending.size() - j.pending_head;
     if (have >= need) return true;
@@ -380,7 +427,6 @@ struct Engine {
     }
     const size_t add = need - have;
     // keep every mark from the newest one that is not ahead of the consumed position: settle_rng restarts from it
-    // (`consumed` only moves between rounds, after the helper threads have been joined)
     size_t keep_from = 0;
     for (size_t i = 0; i < j.marks.size(); ++i)
       if (j.marks[i].first <= j.consumed) keep_from = i;
@@ -400,42 +446,25 @@ struct Engine {
     return true;
   }
 
-  // While the device runs a round: draw the next round's indices for every fit that may need them (a fit consumes
-  // at most one launch's worth per round), spread over host threads. The callback generator is never drawn ahead
-  // (it must be called on the caller's thread, exactly as often as the reference would call it).
-  void prefetch_indices() {
-    std::vector<FitJob*> todo;
-    for (size_t i = 0; i < jobs.size(); ++i) {
-      FitJob& j = jobs[i];
-      if (j.done || args_host[i].n_epochs == 0 || j.rng->kind == SGDNET_RNG_CALLBACK) continue;
-      if (j.rng->kind == SGDNET_RNG_SEQUENCE &&
-          j.rng->seq_len - j.rng->seq_pos < static_cast<int64_t>(2 * size_t(j.epochs_per_launch) * j.dev.n)) continue;
-      todo.push_back(&j);
-    }
-    if (todo.empty()) return;
-    const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    const int K = static_cast<int>(std::min<size_t>(hc, todo.size()));
-    auto work = [&](int k) {
-      for (size_t q = k; q < todo.size(); q += K) {
-        FitJob& j = *todo[q];
-        (void)ensure_pending(j, 2 * size_t(j.epochs_per_launch) * j.dev.n);
-      }
-    };
-    if (K == 1) {
-      work(0);
-      return;
-    }
-    std::vector<std::thread> th;
-    for (int k = 1; k < K; ++k) th.emplace_back(work, k);
-    work(0);
-    for (auto& t : th) t.join();
-  }
-
   // Give the caller's generator back advanced by exactly the draws the fit consumed.
   void settle_rng(FitJob& j) {
+    if (j.device_rng) {
+      // the state the next launch would have started from: snapshot `epochs used` of the last launch
+      if (j.cur_state == nullptr) return;
+      CK(cudaMemcpyAsync(j.rng_pin, j.cur_state, sizeof(MtState), cudaMemcpyDeviceToHost, j.st));
+      CK(cudaStreamSynchronize(j.st));
+      std::memcpy(j.rng->mt, j.rng_pin->mt, sizeof(j.rng->mt));
+      j.rng->mti = j.rng_pin->mti;
+      j.handed_back = *j.rng;
+      j.have_handed_back = true;
+      return;
+    }
     if (j.generated == j.consumed) return;
     if (j.rng->kind == SGDNET_RNG_SEQUENCE) {
       j.rng->seq_pos -= static_cast<int64_t>(j.generated - j.consumed);
+      j.generated = j.consumed;
+      j.pending.clear();
+      j.pending_head = 0;
       return;
     }
     if (j.rng->kind == SGDNET_RNG_CALLBACK) return;   // epochs_per_launch == 1: nothing was drawn ahead
@@ -446,77 +475,225 @@ struct Engine {
         j.rng->unif_rand = keep.unif_rand;
         j.rng->ctx = keep.ctx;
         for (uint64_t q = j.marks[i].first; q < j.consumed; ++q) (void)mt_unif(j.rng);
+        j.generated = j.consumed;
+        j.pending.clear();
+        j.pending_head = 0;
+        j.marks.clear();
         return;
       }
     }
     throw std::runtime_error("internal: no generator mark at or before the consumed position");
   }
 
-  // ---------------------------------------------------------------------------------- rounds
-  // Runs every job to the end of its path (or, with `only_lambda` >= 0, until that lambda is finished).
-  void run(int only_lambda = -1) {
-    const int nf = static_cast<int>(jobs.size());
-    for (;;) {
-      int active = 0;
-      for (int i = 0; i < nf; ++i) {
-        FitJob& j = jobs[i];
-        const Progress& pg = prog_host[i];
-        const bool stop_here = (only_lambda >= 0 && pg.lambda_ind > only_lambda);
-        if (j.done || pg.status == kFitDone || stop_here) {
-          args_host[i] = RoundArgs{nullptr, nullptr, nullptr, 0, 0};
-          continue;
-        }
-        const uint32_t left = j.plan.max_iter - pg.it_outer;
-        const int ne = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(j.epochs_per_launch), std::max<uint32_t>(left, 1u)));
+  // ---------------------------------------------------------------------------------- launches of one fit
+  int deps_ctas() const {
+    int active = 0;
+    for (const FitJob& j : jobs) active += (j.phase != Phase::Done && j.phase != Phase::Parked) ? 1 : 0;
+    return std::max(8, sms * 6 / std::max(1, active));
+  }
+
+  // the caller's generator -> device, at the start of run(); a launch prepared ahead stays valid when the caller hands
+  // back the generator exactly as it received it
+  void upload_rng(FitJob& j) {
+    if (!j.device_rng) return;
+    const bool same = j.have_handed_back && j.rng->mti == j.handed_back.mti &&
+                      std::memcmp(j.rng->mt, j.handed_back.mt, sizeof(j.rng->mt)) == 0;
+    if (same && j.cur_state != nullptr) return;
+    CK(cudaStreamSynchronize(j.st_prep));
+    std::memcpy(j.rng_pin->mt, j.rng->mt, sizeof(j.rng->mt));
+    j.rng_pin->mti = j.rng->mti;
+    CK(cudaMemcpyAsync(j.rng_dev, j.rng_pin, sizeof(MtState), cudaMemcpyHostToDevice, j.st));
+    j.cur_state = j.rng_dev;
+    j.prepped = false;
+    j.prepped_next = false;
+  }
+
+  // `ne_fixed` > 0: measurement mode, run exactly that many epochs (<= epochs_per_launch)
+  void submit_solver(FitJob& j, int flags, int ne_fixed = 0) {
+    const Progress pg = *j.mirror;
+    const uint32_t left = j.plan.max_iter - pg.it_outer;
+    const int epl = j.epochs_per_launch;
+    const int ne = ne_fixed > 0 ? ne_fixed
+                                : static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(epl), std::max<uint32_t>(left, 1u)));
+    const int b = j.buf;
+    RoundArgs ra{j.seq_dev[b], j.dep_dev[b], j.dup_dev[b], ne, flags, ++j.round_id, 0u};
+    const int64_t n = j.dev.n;
+    if (j.prepped) {
+      CK(cudaStreamWaitEvent(j.st, j.ev_prep, 0));
+      j.idx_on_prep = true;
+    } else {
+      if (j.stale_prep) {
+        CK(cudaStreamWaitEvent(j.st, j.ev_prep, 0));   // the discarded preparation reads what is rewritten below
+        j.stale_prep = false;
+      }
+      if (j.device_rng) {
+        CK(launch_mt_indices(j.cur_state, static_cast<uint32_t>(n), epl, j.seq_dev[b], j.snap_dev[b], j.st));
+        ++j.launches;
+      } else {
         if (!stage_indices(j, ne)) {
           g_error = "sampling-index source exhausted";
           throw CudaFail{cudaSuccess, "rng"};
         }
-        CK(cudaMemcpyAsync(j.seq_dev, j.seq_pin, size_t(ne) * j.dev.n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        args_host[i] = RoundArgs{j.seq_dev, j.dep_dev, j.dup_dev, ne, 0};
-        ++active;
+        CK(cudaMemcpyAsync(j.seq_dev[b], j.seq_pin, size_t(ne) * n * sizeof(uint32_t), cudaMemcpyHostToDevice, j.st));
       }
-      if (active == 0) break;
-      CK(cudaMemcpyAsync(args_dev, args_host, sizeof(RoundArgs) * nf, cudaMemcpyHostToDevice, stream));
-      if (variant != Variant::Dense) {
-        CK(launch_lag_scaling(nf, fits_dev, prog_dev, stream));
-        ++launches;
+      CK(cudaEventRecord(j.ev_idx, j.st));
+      j.idx_on_prep = false;
+      if (j.variant == Variant::SparseK1) {
+        RoundArgs rd = ra;
+        rd.n_epochs = j.device_rng ? epl : ne;
+        CK(launch_wave_deps(j.dev_ptr, rd, n * rd.n_epochs, deps_ctas(), j.st));
+        ++j.launches;
       }
-      CK(cudaEventRecord(ev0, stream));
-      if (variant == Variant::SparseK1) {
-        CK(launch_wave_deps(nf, fits_dev, prog_dev, args_dev, max_rows_per_launch, sms, stream));
-        ++launches;
+    }
+    if (j.variant != Variant::Dense) {
+      CK(launch_lag_scaling(j.dev_ptr, j.prog_ptr, j.st));
+      ++j.launches;
+    }
+    CK(cudaEventRecord(j.ev0, j.st));
+    if (j.variant == Variant::Dense)
+      CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
+    else
+      CK(launch_saga_sparse(j.variant == Variant::SparseK1, j.dev_ptr, j.prog_ptr, ra, j.st));
+    ++j.launches;
+    CK(cudaEventRecord(j.ev1, j.st));
+    j.ne_submitted = ne;
+    j.prepped = false;
+    j.prepped_next = false;
+    // ---- the next launch's indices and conflict codes, prepared on the second stream while this one runs, on the
+    // assumption that this launch consumes all `ne` epochs (it does unless the lambda converges inside it)
+    if (j.device_rng && !no_overlap) {
+      if (!j.idx_on_prep) CK(cudaStreamWaitEvent(j.st_prep, j.ev_idx, 0));
+      const int nb = b ^ 1;
+      CK(launch_mt_indices(j.snap_dev[b] + ne, static_cast<uint32_t>(n), epl, j.seq_dev[nb], j.snap_dev[nb], j.st_prep));
+      ++j.launches;
+      if (j.variant == Variant::SparseK1) {
+        RoundArgs rd{j.seq_dev[nb], j.dep_dev[nb], j.dup_dev[nb], epl, 0, 0u, 0u};
+        CK(launch_wave_deps(j.dev_ptr, rd, n * epl, deps_ctas(), j.st_prep));
+        ++j.launches;
       }
-      if (variant == Variant::Dense)
-        CK(launch_saga_dense(nf, dense_kts, dense_pens, dense_smem, fits_dev, prog_dev, args_dev, stream));
-      else
-        CK(launch_saga_sparse(nf, variant == Variant::SparseK1, fits_dev, prog_dev, args_dev, stream));
-      ++launches;
-      CK(cudaEventRecord(ev1, stream));
-      if (any_debug) {
-        CK(launch_epoch_loss(nf, fits_dev, prog_dev, args_dev, loss_blocks, stream));
-        launches += 2;
+      CK(cudaEventRecord(j.ev_prep, j.st_prep));
+      j.prepped_next = true;
+    }
+    j.phase = Phase::Solver;
+  }
+
+  void solver_done(FitJob& j) {
+    const Progress pg = *j.mirror;
+    const uint64_t used_epochs = pg.epochs_last_launch;
+    const uint64_t used = used_epochs * uint64_t(j.dev.n);
+    CK(cudaEventSynchronize(j.ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j.ev0, j.ev1));
+    j.seconds_solver += ms * 1e-3;
+    if (trace_rounds)
+      std::fprintf(stderr, "[sgdnet_b200] fit %d: launch %u, %d epochs at lambda %d, solver %.3f ms\n",
+                   static_cast<int>(&j - jobs.data()), j.round_id, static_cast<int>(used_epochs), pg.lambda_ind, ms);
+    if (j.device_rng) {
+      j.cur_state = j.snap_dev[j.buf] + used_epochs;
+      if (j.prepped_next && used_epochs == static_cast<uint64_t>(j.ne_submitted)) {
+        j.buf ^= 1;
+        j.prepped = true;
+      } else if (j.prepped_next) {
+        j.stale_prep = true;
       }
-      CK(launch_finish_lambda(nf, fits_dev, prog_dev, loss_blocks, stream));
-      launches += 2;
-      CK(cudaEventRecord(ev2, stream));
-      CK(cudaMemcpyAsync(prog_host, prog_dev, sizeof(Progress) * nf, cudaMemcpyDeviceToHost, stream));
-      prefetch_indices();
-      CK(cudaStreamSynchronize(stream));
-      float ms_solver = 0.f, ms_dev = 0.f;
-      CK(cudaEventElapsedTime(&ms_solver, ev0, ev1));
-      CK(cudaEventElapsedTime(&ms_dev, ev1, ev2));
-      seconds_solver += ms_solver * 1e-3;
-      seconds_dev += ms_dev * 1e-3;
-      if (trace_rounds) std::fprintf(stderr, "[sgdnet_b200] round: solver %.3f ms, passes %.3f ms, fits active %d\n", ms_solver, ms_dev, active);
-      for (int i = 0; i < nf; ++i) {
-        if (args_host[i].n_epochs == 0) continue;
-        FitJob& j = jobs[i];
-        const uint64_t used = uint64_t(prog_host[i].epochs_last_launch) * uint64_t(j.dev.n);
-        j.pending_head += used;
-        j.consumed += used;
-        if (prog_host[i].status == kFitDone) j.done = true;
+      j.prepped_next = false;
+    } else {
+      j.pending_head += used;
+      j.consumed += used;
+    }
+    j.needs_finish = pg.status == kLambdaDone || (j.dev.debug && used_epochs > 0);
+  }
+
+  void submit_finish(FitJob& j) {
+    ++j.round_id;
+    CK(cudaEventRecord(j.ev_f0, j.st));
+    if (j.dev.debug) {
+      CK(launch_epoch_loss(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.st));
+      j.launches += 2;
+    }
+    CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.round_id, j.st));
+    j.launches += 2;
+    CK(cudaEventRecord(j.ev_f1, j.st));
+    j.phase = Phase::Finish;
+  }
+
+  void finish_done(FitJob& j) {
+    CK(cudaEventSynchronize(j.ev_f1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, j.ev_f0, j.ev_f1));
+    j.seconds_dev += ms * 1e-3;
+    j.needs_finish = false;
+  }
+
+  uint64_t idle_sweeps = 0;
+  void wait_round(FitJob& j) {
+    uint64_t spins = 0;
+    while (*reinterpret_cast<volatile uint32_t*>(&j.mirror->round_seen) != j.round_id) {
+      if (++spins % 4096 == 0) check_in_flight();
+      std::this_thread::yield();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  void check_in_flight() {
+    for (FitJob& j : jobs) {
+      if (j.phase != Phase::Solver && j.phase != Phase::Finish) continue;
+      const cudaError_t e = cudaStreamQuery(j.st);
+      if (e == cudaErrorNotReady) continue;
+      if (e != cudaSuccess) throw CudaFail{e, "a launch of the batch failed"};
+      // the stream has drained: the round must have been published
+      std::atomic_thread_fence(std::memory_order_acquire);
+      if (*reinterpret_cast<volatile uint32_t*>(&j.mirror->round_seen) != j.round_id)
+        throw std::runtime_error("internal: a launch finished without publishing its progress");
+    }
+  }
+
+  // ---------------------------------------------------------------------------------- the event loop
+  // Runs every job to the end of its path (or, with `only_lambda` >= 0, until that lambda is finished). `score`: fits
+  // with held-out rows are scored on their own stream as soon as they are done.
+  void run(int only_lambda = -1, bool score = false) {
+    for (FitJob& j : jobs) {
+      if (j.phase == Phase::Parked) j.phase = Phase::Idle;
+      if (j.phase != Phase::Done) upload_rng(j);
+    }
+    for (;;) {
+      bool progressed = false, any_live = false;
+      for (FitJob& j : jobs) {
+        if (j.phase == Phase::Done || j.phase == Phase::Parked) continue;
+        any_live = true;
+        if (j.phase == Phase::Solver || j.phase == Phase::Finish) {
+          if (*reinterpret_cast<volatile uint32_t*>(&j.mirror->round_seen) != j.round_id) continue;
+          std::atomic_thread_fence(std::memory_order_acquire);
+          if (j.phase == Phase::Solver) solver_done(j);
+          else finish_done(j);
+          j.phase = Phase::Idle;
+        }
+        // Idle: decide the fit's next launch from its published progress
+        const Progress pg = *j.mirror;
+        progressed = true;
+        if (pg.status == kFitDone) {
+          if (score && j.test_rows && j.n_test > 0 && !j.scored) submit_score(j);
+          j.phase = Phase::Done;
+        } else if (j.needs_finish || pg.status == kLambdaDone) {
+          submit_finish(j);
+        } else if (only_lambda >= 0 && pg.lambda_ind > only_lambda) {
+          j.phase = Phase::Parked;
+        } else {
+          submit_solver(j, 0);
+        }
       }
+      if (!any_live) break;
+      if (!progressed) {
+        // nothing finished in this sweep: let the core breathe; now and then make sure the launches in flight are
+        // still alive (a failed launch never publishes its round)
+        if (++idle_sweeps % 4096 == 0) check_in_flight();
+        std::this_thread::yield();
+      } else {
+        idle_sweeps = 0;
+      }
+    }
+    for (FitJob& j : jobs) {
+      CK(cudaStreamSynchronize(j.st));
+      CK(cudaStreamSynchronize(j.st_prep));
     }
   }
 
@@ -563,11 +740,11 @@ struct Engine {
       out->losses = static_cast<double*>(mal(8));
       for (int l = 0; l < L; ++l) out->losses_ptr[l + 1] = 0;
     }
-    out->seconds_solver = seconds_solver;
-    out->seconds_deviance = seconds_dev;
+    out->seconds_solver = j.seconds_solver;
+    out->seconds_deviance = j.seconds_dev;
     out->seconds_setup = seconds_setup;
     out->seconds_total = now_s() - t_begin;
-    out->kernel_launches = launches;
+    out->kernel_launches = j.launches;
   }
 
   // ---------------------------------------------------------------------------------- raw design + scoring
@@ -582,9 +759,9 @@ struct Engine {
     raw_uploaded = true;
   }
 
-  // score/link of rows `row_ids` (device pointer or null) under coefficients (a0_dev, beta_dev)
-  void predict_score(int family, int K, int L, const int32_t* row_ids_dev, int64_t n_rows, const double* a0_dev,
-                     const double* beta_dev, bool with_y, double* link_dev, double* score_dev) {
+  // score/link of rows `row_ids` (device pointer or null) under coefficients (a0_dev, beta_dev), on stream `st`
+  uint64_t predict_score(int family, int K, int L, const int32_t* row_ids_dev, int64_t n_rows, const double* a0_dev,
+                         const double* beta_dev, bool with_y, double* link_dev, double* score_dev, cudaStream_t st) {
     upload_raw();
     const HostDesign& hd = *designs[std::make_pair((const int32_t*)nullptr, 0)].first;
     PredictArgs a{};
@@ -605,15 +782,26 @@ struct Engine {
     a.a0 = a0_dev;
     a.beta = beta_dev;
     a.link = link_dev;
-    int sms = 148, dev_id = 0;
-    cudaGetDevice(&dev_id);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(int64_t(sms) * 4, (n_rows + 7) / 8)));
-    a.partials = arena.alloc<double>(size_t(blocks) * L);
+    a.partials = arena.alloc<double>(size_t(blocks) * L, false);     // every entry is written by its block
     a.score = score_dev;
     double* bt = arena.alloc<double>(size_t(hd.p) * L * K, false);
-    CK(launch_predict_score(a, bt, blocks, stream));
-    launches += score_dev ? 3 : 2;
+    CK(launch_predict_score(a, bt, blocks, st));
+    return score_dev ? 3 : 2;
+  }
+
+  // score(fit, x_test, y_test) of a finished fit, on the fit's own stream (R/cv_sgdnet.R:197-198)
+  void submit_score(FitJob& j) {
+    int32_t*& td = test_dev[j.test_rows];
+    if (!td) {
+      td = arena.alloc<int32_t>(j.n_test, false);
+      CK(cudaMemcpy(td, j.test_rows, sizeof(int32_t) * j.n_test, cudaMemcpyHostToDevice));
+    }
+    const int L = j.plan.n_lambda;
+    j.score_dev = arena.alloc<double>(L, false);
+    j.launches += predict_score(j.plan.family, j.plan.K, L, td, j.n_test, j.dev.a0_arch, j.dev.beta_arch, true, nullptr,
+                                j.score_dev, j.st);
+    j.scored = true;
   }
 };
 
@@ -691,69 +879,84 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
   if (!specs || n_fits <= 0 || !results) return fail(SGDNET_ERR_ARG, "null specs/results or no fits");
   if (!basic_args(xa.n, xa.p, y, y_cols, why)) return fail(SGDNET_ERR_ARG, why);
   return guarded([&]() -> int {
-    // group fits by kernel variant; each group is one batch of concurrent CTAs
-    std::vector<int> order(n_fits);
-    for (int i = 0; i < n_fits; ++i) order[i] = i;
-    auto variant_of = [&](const sgdnet_fit_spec& s) {
-      if (!xa.sparse) return s.control.n_classes == 1 ? 0 : 1;
-      return (s.control.n_classes == 1 && !s.control.standardize) ? 2 : 3;
-    };
     // row stride of `scores`: the caller sizes it from the controls it passed. A fit's resolved path never has more
     // than its own (or, with lambda_from, its source's) control.n_lambda values: FitPlan::build truncates a longer
     // given sequence to n_lambda.
     int max_lambda = 0;
     for (int i = 0; i < n_fits; ++i) max_lambda = std::max(max_lambda, specs[i].control.n_lambda);
-    for (int v = 0; v < 4; ++v) {
-      std::vector<int> group;
+    for (int i = 0; i < n_fits; ++i) {
+      const sgdnet_fit_spec& s = specs[i];
+      if (s.lambda_from >= i) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": lambda_from must name an earlier fit");
+      if (s.test_rows)
+        for (int64_t q = 0; q < s.n_test; ++q)
+          if (s.test_rows[q] < 0 || s.test_rows[q] >= xa.n) return fail(SGDNET_ERR_ARG, "test row id out of range");
+    }
+    // ONE engine for the whole batch: every fit is its own pipeline, whatever its kernel variant
+    Engine eng;
+    load_x(eng, xa, y, y_cols);
+    // 1. designs (one per distinct row subset x standardize), serial
+    for (int i = 0; i < n_fits; ++i) {
+      sgdnet_fit_spec& s = specs[i];
+      std::string err = eng.add_fit_design(s.train_rows, s.n_train, s.control, &s.rng, s.test_rows, s.n_test, 0);
+      if (!err.empty()) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + err);
+    }
+    // 2. plans (response statistics, lambda path, step sizes) on the host cores, independent fits concurrently; a fit
+    //    that takes its path from an earlier one (`lambda = lambda[[i]]`, R/cv_sgdnet.R:164, 186) goes in a later wave
+    PhaseTimer pt;
+    std::vector<std::string> errs(n_fits);
+    std::vector<int> wave(n_fits, 0);
+    int n_waves = 1;
+    for (int i = 0; i < n_fits; ++i)
+      if (specs[i].lambda_from >= 0) {
+        wave[i] = wave[specs[i].lambda_from] + 1;
+        n_waves = std::max(n_waves, wave[i] + 1);
+      }
+    for (int w = 0; w < n_waves; ++w) {
+      std::vector<int> todo;
       for (int i = 0; i < n_fits; ++i)
-        if (variant_of(specs[i]) == v) group.push_back(i);
-      if (group.empty()) continue;
-      Engine eng;
-      load_x(eng, xa, y, y_cols);
-      std::map<int, int> job_of;   // spec index -> job index inside this engine
-      for (int i : group) {
-        sgdnet_fit_spec& s = specs[i];
-        sgdnet_control ctl = s.control;
-        if (s.lambda_from >= 0) {
-          // lambda = the path of an earlier fit of the batch (R/cv_sgdnet.R:164, 186), known after that fit's setup
-          auto src = job_of.find(s.lambda_from);
-          if (s.lambda_from >= i || src == job_of.end())
-            return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": lambda_from must name an earlier fit of the same kind");
-          const std::vector<double>& lam = eng.jobs[src->second].plan.lambda;
-          ctl.lambda = lam.data();
-          ctl.lambda_len = static_cast<int32_t>(lam.size());
-          ctl.n_lambda = ctl.lambda_len;
-        }
-        std::string err = eng.add_fit(s.train_rows, s.n_train, ctl, &s.rng, s.test_rows, s.n_test);
-        if (!err.empty()) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + err);
-        job_of[i] = static_cast<int>(eng.jobs.size()) - 1;
-      }
-      eng.finalize_batch();
-      eng.run();
-      for (size_t g = 0; g < group.size(); ++g) {
-        eng.settle_rng(eng.jobs[g]);
-        eng.fill_result(static_cast<int>(g), &results[group[g]]);
-      }
-      if (scores) {
-        // score(fit, x_test, y_test, "deviance") for every fit with held-out rows (R/cv_sgdnet.R:197-198)
-        std::map<const int32_t*, int32_t*> test_dev;
-        for (size_t g = 0; g < group.size(); ++g) {
-          FitJob& j = eng.jobs[g];
-          if (!j.test_rows || j.n_test <= 0) continue;
-          for (int64_t q = 0; q < j.n_test; ++q)
-            if (j.test_rows[q] < 0 || j.test_rows[q] >= xa.n) return fail(SGDNET_ERR_ARG, "test row id out of range");
-          int32_t*& td = test_dev[j.test_rows];
-          if (!td) {
-            td = eng.arena.alloc<int32_t>(j.n_test, false);
-            CK(cudaMemcpy(td, j.test_rows, sizeof(int32_t) * j.n_test, cudaMemcpyHostToDevice));
+        if (wave[i] == w) todo.push_back(i);
+      std::atomic<size_t> next{0};
+      auto work = [&]() {
+        for (;;) {
+          const size_t q = next.fetch_add(1);
+          if (q >= todo.size()) break;
+          const int i = todo[q];
+          sgdnet_control ctl = specs[i].control;
+          if (specs[i].lambda_from >= 0) {
+            const std::vector<double>& lam = eng.jobs[specs[i].lambda_from].plan.lambda;
+            ctl.lambda = lam.data();
+            ctl.lambda_len = static_cast<int32_t>(lam.size());
+            ctl.n_lambda = ctl.lambda_len;
           }
-          const int L = j.plan.n_lambda;
-          double* score_dev = eng.arena.alloc<double>(L);
-          eng.predict_score(j.plan.family, j.plan.K, L, td, j.n_test, j.dev.a0_arch, j.dev.beta_arch, true, nullptr, score_dev);
-          CK(cudaStreamSynchronize(eng.stream));
-          CK(cudaMemcpy(scores + size_t(group[g]) * max_lambda, score_dev, sizeof(double) * std::min(L, max_lambda), cudaMemcpyDeviceToHost));
+          try {
+            errs[i] = eng.build_plan(eng.jobs[i], specs[i].train_rows, ctl);
+          } catch (const std::exception& e) {
+            errs[i] = e.what();
+          }
         }
-      }
+      };
+      const unsigned hc = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      const size_t nt = std::min<size_t>(hc, todo.size());
+      std::vector<std::thread> th;
+      for (size_t k = 1; k < nt; ++k) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+      for (int i : todo)
+        if (!errs[i].empty()) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + errs[i]);
+    }
+    pt.lap("plans (all fits)");
+    // 3. device state
+    for (int i = 0; i < n_fits; ++i) eng.alloc_fit(eng.jobs[i]);
+    pt.lap("state alloc + upload (all fits)");
+    eng.finalize_batch();
+    eng.run(-1, scores != nullptr);
+    for (int i = 0; i < n_fits; ++i) {
+      eng.settle_rng(eng.jobs[i]);
+      eng.fill_result(i, &results[i]);
+      FitJob& j = eng.jobs[i];
+      if (scores && j.scored)
+        CK(cudaMemcpy(scores + size_t(i) * max_lambda, j.score_dev, sizeof(double) * std::min(j.plan.n_lambda, max_lambda),
+                      cudaMemcpyDeviceToHost));
     }
     return SGDNET_OK;
   });
@@ -771,7 +974,7 @@ int predict_or_score(const XArg& xa, const double* y, int32_t y_cols, int32_t fa
     double* bd = eng.arena.upload(bv);
     double* link_dev = link ? eng.arena.alloc<double>(size_t(L) * K * xa.n, false) : nullptr;
     double* score_dev = score ? eng.arena.alloc<double>(L) : nullptr;
-    eng.predict_score(family, K, L, nullptr, xa.n, a0d, bd, score != nullptr, link_dev, score_dev);
+    eng.predict_score(family, K, L, nullptr, xa.n, a0d, bd, score != nullptr, link_dev, score_dev, eng.stream);
     CK(cudaStreamSynchronize(eng.stream));
     if (link) CK(cudaMemcpy(link, link_dev, sizeof(double) * size_t(L) * K * xa.n, cudaMemcpyDeviceToHost));
     if (score) CK(cudaMemcpy(score, score_dev, sizeof(double) * L, cudaMemcpyDeviceToHost));
@@ -799,6 +1002,45 @@ void sgdnet_rng_set_seed(sgdnet_rng* rng, uint32_t seed) {
   mt_seed(rng, seed);
 }
 double sgdnet_rng_unif(sgdnet_rng* rng) { return mt_unif(rng); }
+
+int sgdnet_rng_indices(sgdnet_rng* rng, uint32_t n, int32_t n_epochs, uint32_t* seq, sgdnet_rng* states, int32_t on_host) {
+  if (!rng || !seq || n == 0 || n_epochs <= 0) return fail(SGDNET_ERR_ARG, "bad rng_indices arguments");
+  if (rng->kind != SGDNET_RNG_MT) return fail(SGDNET_ERR_ARG, "rng_indices needs an SGDNET_RNG_MT generator");
+  return guarded([&]() -> int {
+    MtState src{};
+    std::memcpy(src.mt, rng->mt, sizeof(src.mt));
+    src.mti = rng->mti;
+    std::vector<MtState> snaps(size_t(n_epochs) + 1);
+    const size_t total = size_t(n) * n_epochs;
+    if (on_host) {
+      mt_indices_host(&src, n, n_epochs, seq, snaps.data());
+    } else {
+      int count = 0;
+      if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaFail{cudaErrorNoDevice, "no CUDA device (no CPU fallback)"};
+      Arena arena;
+      MtState* src_d = arena.upload_from(&src, 1);
+      MtState* snaps_d = arena.alloc<MtState>(snaps.size(), false);
+      uint32_t* seq_d = arena.alloc<uint32_t>(total, false);
+      CK(launch_mt_indices(src_d, n, n_epochs, seq_d, snaps_d, nullptr));
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(seq, seq_d, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(snaps.data(), snaps_d, sizeof(MtState) * snaps.size(), cudaMemcpyDeviceToHost));
+    }
+    for (int e = 0; e <= n_epochs; ++e) {
+      sgdnet_rng* dst = (e == n_epochs) ? rng : nullptr;
+      if (states) {
+        states[e] = *rng;
+        std::memcpy(states[e].mt, snaps[e].mt, sizeof(snaps[e].mt));
+        states[e].mti = snaps[e].mti;
+      }
+      if (dst) {
+        std::memcpy(dst->mt, snaps[e].mt, sizeof(snaps[e].mt));
+        dst->mti = snaps[e].mti;
+      }
+    }
+    return SGDNET_OK;
+  });
+}
 
 void sgdnet_result_free(sgdnet_result* r) {
   if (!r) return;
@@ -913,43 +1155,27 @@ int sgdnet_session_run_epochs(sgdnet_session* s, int32_t lambda_ind, int32_t n_e
     FitJob& j = e.jobs[0];
     if (lambda_ind < 0 || lambda_ind >= j.plan.n_lambda) return fail(SGDNET_ERR_ARG, "lambda index out of range");
     j.rng = rng;
+    if (j.device_rng != (rng->kind == SGDNET_RNG_MT && !e.host_rng)) return fail(SGDNET_ERR_ARG, "session created for another generator kind");
+    e.upload_rng(j);
     // measurement mode: run exactly n_epochs at lambda_ind, never leave kRunning
-    float total_ms = 0.f;
+    const double solver_before = j.seconds_solver;
     int left = n_epochs;
     while (left > 0) {
       const int ne = std::min(left, j.epochs_per_launch);
-      e.prog_host[0].lambda_ind = lambda_ind;
-      e.prog_host[0].status = kRunning;
-      e.prog_host[0].it_outer = (e.prog_host[0].it_outer == 0) ? 0u : 1u;   // keep "new lambda" only for the first call
-      CK(cudaMemcpyAsync(e.prog_dev, e.prog_host, sizeof(Progress), cudaMemcpyHostToDevice, e.stream));
-      if (!e.stage_indices(j, ne)) return fail(SGDNET_ERR_RNG, "sampling-index source exhausted");
-      CK(cudaMemcpyAsync(j.seq_dev, j.seq_pin, size_t(ne) * j.dev.n * sizeof(uint32_t), cudaMemcpyHostToDevice, e.stream));
-      e.args_host[0] = RoundArgs{j.seq_dev, j.dep_dev, j.dup_dev, ne, 1};
-      CK(cudaMemcpyAsync(e.args_dev, e.args_host, sizeof(RoundArgs), cudaMemcpyHostToDevice, e.stream));
-      if (e.variant != Variant::Dense) { CK(launch_lag_scaling(1, e.fits_dev, e.prog_dev, e.stream)); ++e.launches; }
-      CK(cudaEventRecord(e.ev0, e.stream));
-      if (e.variant == Variant::SparseK1) {
-        CK(launch_wave_deps(1, e.fits_dev, e.prog_dev, e.args_dev, e.max_rows_per_launch, e.sms, e.stream));
-        ++e.launches;
-      }
-      if (e.variant == Variant::Dense)
-        CK(launch_saga_dense(1, e.dense_kts, e.dense_pens, e.dense_smem, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
-      else
-        CK(launch_saga_sparse(1, e.variant == Variant::SparseK1, e.fits_dev, e.prog_dev, e.args_dev, e.stream));
-      ++e.launches;
-      CK(cudaEventRecord(e.ev1, e.stream));
-      CK(cudaMemcpyAsync(e.prog_host, e.prog_dev, sizeof(Progress), cudaMemcpyDeviceToHost, e.stream));
-      CK(cudaStreamSynchronize(e.stream));
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, e.ev0, e.ev1));
-      total_ms += ms;
-      j.pending_head += size_t(ne) * j.dev.n;
-      j.consumed += uint64_t(ne) * j.dev.n;
-      e.prog_host[0].it_outer = 1;
+      j.mirror->lambda_ind = lambda_ind;
+      j.mirror->status = kRunning;
+      j.mirror->it_outer = (j.mirror->it_outer == 0) ? 0u : 1u;   // keep "new lambda" only for the first call
+      CK(cudaMemcpyAsync(j.prog_ptr, j.mirror, sizeof(Progress), cudaMemcpyHostToDevice, j.st));
+      e.submit_solver(j, 1, ne);
+      e.wait_round(j);
+      e.solver_done(j);
+      j.needs_finish = false;
+      j.phase = Phase::Idle;
+      j.mirror->it_outer = 1;
       left -= ne;
     }
-    e.seconds_solver += total_ms * 1e-3;
-    if (device_ms) *device_ms = total_ms;
+    e.settle_rng(j);
+    if (device_ms) *device_ms = static_cast<float>((j.seconds_solver - solver_before) * 1e3);
     return SGDNET_OK;
   });
 }
@@ -959,14 +1185,11 @@ int sgdnet_session_fit_lambda(sgdnet_session* s, int32_t lambda_ind, sgdnet_rng*
   return guarded([&]() -> int {
     Engine& e = s->eng;
     FitJob& j = e.jobs[0];
-    if (lambda_ind != e.prog_host[0].lambda_ind) return fail(SGDNET_ERR_ARG, "lambdas must be fitted in path order");
+    if (lambda_ind != j.mirror->lambda_ind) return fail(SGDNET_ERR_ARG, "lambdas must be fitted in path order");
     j.rng = rng;
+    if (j.device_rng != (rng->kind == SGDNET_RNG_MT && !e.host_rng)) return fail(SGDNET_ERR_ARG, "session created for another generator kind");
     e.run(lambda_ind);
     e.settle_rng(j);
-    j.pending.clear();
-    j.pending_head = 0;
-    j.generated = j.consumed;
-    j.marks.clear();
     uint32_t ep = 0, code = 0;
     CK(cudaMemcpy(&ep, j.dev.epochs + lambda_ind, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&code, j.dev.codes + lambda_ind, sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -980,20 +1203,17 @@ int sgdnet_session_finish_lambda(sgdnet_session* s, int32_t lambda_ind, float* d
   if (!s) return fail(SGDNET_ERR_ARG, "null session");
   return guarded([&]() -> int {
     Engine& e = s->eng;
+    FitJob& j = e.jobs[0];
     // measurement entry: force the deviance + rescale pass for lambda_ind on the current state
-    e.prog_host[0].lambda_ind = lambda_ind;
-    e.prog_host[0].status = kLambdaDone;
-    CK(cudaMemcpyAsync(e.prog_dev, e.prog_host, sizeof(Progress), cudaMemcpyHostToDevice, e.stream));
-    CK(cudaEventRecord(e.ev0, e.stream));
-    CK(launch_finish_lambda(1, e.fits_dev, e.prog_dev, e.loss_blocks, e.stream));
-    e.launches += 2;
-    CK(cudaEventRecord(e.ev1, e.stream));
-    CK(cudaMemcpyAsync(e.prog_host, e.prog_dev, sizeof(Progress), cudaMemcpyDeviceToHost, e.stream));
-    CK(cudaStreamSynchronize(e.stream));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e.ev0, e.ev1));
-    e.seconds_dev += ms * 1e-3;
-    if (device_ms) *device_ms = ms;
+    j.mirror->lambda_ind = lambda_ind;
+    j.mirror->status = kLambdaDone;
+    CK(cudaMemcpyAsync(j.prog_ptr, j.mirror, sizeof(Progress), cudaMemcpyHostToDevice, j.st));
+    const double before = j.seconds_dev;
+    e.submit_finish(j);
+    e.wait_round(j);
+    e.finish_done(j);
+    j.phase = Phase::Idle;
+    if (device_ms) *device_ms = static_cast<float>((j.seconds_dev - before) * 1e3);
     return SGDNET_OK;
   });
 }

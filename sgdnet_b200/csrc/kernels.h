@@ -14,27 +14,41 @@ struct RoundArgs {
   uint8_t* dup;          // sparse K == 1: [n * n_epochs] distance to the last in-window row of the same sample
   int32_t n_epochs;      // epochs this launch may run (0 => the fit sits this round out)
   int32_t flags;         // bit 0: measurement mode - run exactly n_epochs, ignore convergence, stay kRunning
+  uint32_t round_id;     // published with the fit's Progress when the launch is over (publish_progress)
+  uint32_t pad_;
 };
 
-// SAGA epochs, one CTA per fit (saga_dense.cu / saga_sparse.cu).
+// Every launcher below works on ONE fit (its FitDev / Progress in device memory) on the stream it is given: the engine
+// runs each fit of a batch as its own asynchronous pipeline (engine.cu).
+
+// SAGA epochs, one persistent CTA per fit (saga_dense.cu / saga_sparse.cu).
 size_t dense_smem_bytes(int K, int p, int ld, int* state_in_smem);
 size_t dense_smem_budget();
-cudaError_t launch_saga_dense(int n_fits, unsigned kts, unsigned pens, size_t smem, FitDev* fits, Progress* prog,
-                              const RoundArgs* args, cudaStream_t st);
+cudaError_t launch_saga_dense(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 int dense_kt_bucket(int K);   // 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for
-cudaError_t launch_saga_sparse(int n_fits, bool fast_k1, FitDev* fits, Progress* prog, const RoundArgs* args,
-                               cudaStream_t st);
+cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 
-// Conflict codes of the staged sequences for the wavefront kernel (sparse K == 1); must precede launch_saga_sparse.
-cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* prog, const RoundArgs* args,
-                             int64_t max_rows, int sms, cudaStream_t st);
+// Conflict codes of a staged sequence for the wavefront kernel (sparse K == 1); a function of the sequence alone, so it
+// may run ahead of the solver launch that consumes it.
+cudaError_t launch_wave_deps(const FitDev* fit, const RoundArgs& ra, int64_t rows, int ctas, cudaStream_t st);
 int wave_warps();
 
+// R's Mersenne-Twister on the device (rng.cu): the sampling sequence of `n_epochs` epochs, floor(n * unif_rand()) per
+// update (src/saga-sparse.h:261, src/saga-dense.h:152), from the generator state `src`; snaps[e] is the generator after
+// e epochs (snaps[0] == *src), which is where the next launch resumes when the solver stopped after e epochs.
+struct MtState {
+  uint32_t mt[624];
+  int32_t mti;
+  int32_t pad_[3];
+};
+cudaError_t launch_mt_indices(const MtState* src, uint32_t n, int n_epochs, uint32_t* seq, MtState* snaps, cudaStream_t st);
+// the same block regeneration on the host, for the CPU unit test of the parallel schedule (tests/test_abi_cpu.py)
+void mt_indices_host(const MtState* src, uint32_t n, int n_epochs, uint32_t* seq, MtState* snaps);
+
 // passes.cu
-cudaError_t launch_lag_scaling(int n_fits, FitDev* fits, Progress* prog, cudaStream_t st);
-cudaError_t launch_finish_lambda(int n_fits, FitDev* fits, Progress* prog, int blocks_per_fit, cudaStream_t st);
-cudaError_t launch_epoch_loss(int n_fits, FitDev* fits, Progress* prog, const RoundArgs* args, int blocks_per_fit,
-                              cudaStream_t st);
+cudaError_t launch_lag_scaling(FitDev* fit, Progress* prog, cudaStream_t st);
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, uint32_t round_id, cudaStream_t st);
+cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st);
 
 struct PredictArgs {
   int32_t sparse, family, K, Ky, p, ld, n_lambda, pad_;

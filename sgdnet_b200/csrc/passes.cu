@@ -18,11 +18,10 @@ namespace sgd {
 constexpr int kPassThreads = 256;
 
 // ------------------------------------------------------------------------------------------ lag scaling
-__global__ void lag_scaling_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog) {
-  const int fit_id = blockIdx.x;
-  const Progress& pg = prog[fit_id];
+__global__ void lag_scaling_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog) {
+  const Progress& pg = *prog;
   if (pg.status != kRunning || pg.it_outer != 0) return;
-  const FitDev& f = fits[fit_id];
+  const FitDev& f = *fit;
   if (!f.sparse || threadIdx.x != 0) return;
   const int li = pg.lambda_ind;
   const double r = 1.0 - f.alpha[li] * f.gamma[li];
@@ -39,8 +38,8 @@ __global__ void lag_scaling_kernel(FitDev* __restrict__ fits, const Progress* __
   }
 }
 
-cudaError_t launch_lag_scaling(int n_fits, FitDev* fits, Progress* prog, cudaStream_t st) {
-  lag_scaling_kernel<<<n_fits, 32, 0, st>>>(fits, prog);
+cudaError_t launch_lag_scaling(FitDev* fit, Progress* prog, cudaStream_t st) {
+  lag_scaling_kernel<<<1, 32, 0, st>>>(fit, prog);
   return cudaGetLastError();
 }
 
@@ -68,15 +67,13 @@ __device__ __forceinline__ double sample_loss_warp(const FitDev& f, int K, int K
 }
 
 __global__ void __launch_bounds__(kPassThreads)
-loss_pass_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
-                 int mode) {
+loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode) {
   __shared__ double wc_s[32];
   __shared__ double red_s[kPassThreads / 32];
   __shared__ double red2[2 * (kPassThreads / 32) * 32];
-  const int fit_id = blockIdx.y;
-  const Progress& pg = prog[fit_id];
-  const FitDev& f = fits[fit_id];
-  if (mode == 0 ? (pg.status != kLambdaDone) : (args[fit_id].n_epochs == 0 || !f.debug)) return;
+  const Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (mode == 0 ? (pg.status != kLambdaDone) : !f.debug) return;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int K = f.K, Ky = f.Ky, p = f.p, ld = f.ld;
@@ -145,13 +142,15 @@ loss_pass_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog, c
 
 // ------------------------------------------------------------------------------------------ finish lambda
 __global__ void __launch_bounds__(kPassThreads)
-finish_lambda_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, int n_partials) {
+finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int n_partials, uint32_t round_id) {
   __shared__ double red[(kPassThreads / 32) * 32];
   __shared__ double xbs[32];
-  const int fit_id = blockIdx.x;
-  Progress& pg = prog[fit_id];
-  if (pg.status != kLambdaDone) return;
-  const FitDev& f = fits[fit_id];
+  Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (pg.status != kLambdaDone) {
+    if (threadIdx.x == 0) publish_progress(f.mirror, pg, round_id);
+    return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int K = f.K, p = f.p;
   const int li = pg.lambda_ind;
@@ -186,38 +185,34 @@ finish_lambda_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, int
     pg.lambda_ind = li + 1;
     pg.it_outer = 0;
     pg.status = (li + 1 >= f.n_lambda) ? kFitDone : kRunning;
+    publish_progress(f.mirror, pg, round_id);
   }
 }
 
-cudaError_t launch_finish_lambda(int n_fits, FitDev* fits, Progress* prog, int blocks_per_fit, cudaStream_t st) {
-  dim3 grid(blocks_per_fit, n_fits);
-  loss_pass_kernel<<<grid, kPassThreads, 0, st>>>(fits, prog, nullptr, 0);
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, uint32_t round_id, cudaStream_t st) {
+  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  finish_lambda_kernel<<<n_fits, kPassThreads, 0, st>>>(fits, prog, blocks_per_fit);
+  finish_lambda_kernel<<<1, kPassThreads, 0, st>>>(fit, prog, blocks, round_id);
   return cudaGetLastError();
 }
 
 // debug: per-epoch mean loss appended to f.losses[lambda_ind * max_iter + it_outer - 1]
-__global__ void store_epoch_loss_kernel(FitDev* __restrict__ fits, const Progress* __restrict__ prog,
-                                        const RoundArgs* __restrict__ args, int n_partials) {
-  const int fit_id = blockIdx.x;
-  const Progress& pg = prog[fit_id];
-  const FitDev& f = fits[fit_id];
-  if (args[fit_id].n_epochs == 0 || !f.debug || threadIdx.x != 0) return;
+__global__ void store_epoch_loss_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int n_partials) {
+  const Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (!f.debug || threadIdx.x != 0) return;
   double loss = 0.0;
   for (int i = 0; i < n_partials; ++i) loss += f.partials[i];
   // after an epoch the fit is either still running at lambda_ind, or it just finished lambda_ind (status LambdaDone)
   f.losses[size_t(pg.lambda_ind) * f.max_iter + (pg.it_outer - 1)] = loss;
 }
 
-cudaError_t launch_epoch_loss(int n_fits, FitDev* fits, Progress* prog, const RoundArgs* args, int blocks_per_fit,
-                              cudaStream_t st) {
-  dim3 grid(blocks_per_fit, n_fits);
-  loss_pass_kernel<<<grid, kPassThreads, 0, st>>>(fits, prog, args, 1);
+cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st) {
+  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  store_epoch_loss_kernel<<<n_fits, 32, 0, st>>>(fits, prog, args, blocks_per_fit);
+  store_epoch_loss_kernel<<<1, 32, 0, st>>>(fit, prog, blocks);
   return cudaGetLastError();
 }
 

@@ -69,15 +69,18 @@ size_t dense_smem_budget() { return 227 * 1024; }
 // interleaved (one butterfly's latency instead of K of them) and the coefficient sweep is straight-line code.
 template <int KT, int PEN>
 __global__ void __launch_bounds__(kDenseThreads, 1)
-saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const RoundArgs* __restrict__ args) {
+saga_dense_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool kScalar = (KT == 1);
-  const int fit_id = blockIdx.x;
-  const RoundArgs ra = args[fit_id];
-  Progress& pg = prog[fit_id];
-  if (ra.n_epochs <= 0 || pg.status != kRunning) return;
-  const FitDev& f = fits[fit_id];
-  if (f.penalty != PEN || (kScalar ? f.K != 1 : (f.K <= KT / 2 && KT > 4) || f.K > KT || f.K == 1)) return;   // another instantiation's fit
+  Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (ra.n_epochs <= 0 || pg.status != kRunning) {
+    if (threadIdx.x == 0) {
+      pg.epochs_last_launch = 0;
+      publish_progress(f.mirror, pg, ra.round_id);
+    }
+    return;
+  }
   const bool free_run = (ra.flags & 1) != 0;
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
@@ -379,41 +382,38 @@ saga_dense_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const 
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    publish_progress(f.mirror, pg, ra.round_id);
   }
 }
 
 template <int KT, int PEN>
-static cudaError_t launch_dense_variant(int n_fits, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
-                                        cudaStream_t st) {
+static cudaError_t launch_dense_variant(size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(saga_dense_kernel<KT, PEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  saga_dense_kernel<KT, PEN><<<n_fits, kDenseThreads, smem, st>>>(fits, prog, args);
+  saga_dense_kernel<KT, PEN><<<1, kDenseThreads, smem, st>>>(fit, prog, ra);
   return cudaGetLastError();
 }
 
 template <int KT>
-static cudaError_t launch_dense_kt(unsigned pens, int n_fits, size_t smem, FitDev* fits, Progress* prog, const RoundArgs* args,
-                                   cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
-  if ((pens & (1u << kRidge)) && e == cudaSuccess) e = launch_dense_variant<KT, kRidge>(n_fits, smem, fits, prog, args, st);
-  if ((pens & (1u << kElasticNet)) && e == cudaSuccess) e = launch_dense_variant<KT, kElasticNet>(n_fits, smem, fits, prog, args, st);
-  if ((pens & (1u << kGroupLasso)) && e == cudaSuccess) e = launch_dense_variant<KT, kGroupLasso>(n_fits, smem, fits, prog, args, st);
-  return e;
-}
-
-// One launch per (class-count bucket, penalty) present in the batch; a CTA whose fit belongs to another
-// instantiation returns at once. `kts` / `pens`: bit masks of the buckets (the bucket value itself) and penalties present.
-cudaError_t launch_saga_dense(int n_fits, unsigned kts, unsigned pens, size_t smem, FitDev* fits, Progress* prog,
-                              const RoundArgs* args, cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
-  if ((kts & 1u) && e == cudaSuccess) e = launch_dense_kt<1>(pens, n_fits, smem, fits, prog, args, st);
-  if ((kts & 4u) && e == cudaSuccess) e = launch_dense_kt<4>(pens, n_fits, smem, fits, prog, args, st);
-  if ((kts & 8u) && e == cudaSuccess) e = launch_dense_kt<8>(pens, n_fits, smem, fits, prog, args, st);
-  if ((kts & 16u) && e == cudaSuccess) e = launch_dense_kt<16>(pens, n_fits, smem, fits, prog, args, st);
-  if ((kts & 32u) && e == cudaSuccess) e = launch_dense_kt<32>(pens, n_fits, smem, fits, prog, args, st);
-  return e;
+static cudaError_t launch_dense_kt(int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  switch (pen) {
+    case kRidge: return launch_dense_variant<KT, kRidge>(smem, fit, prog, ra, st);
+    case kElasticNet: return launch_dense_variant<KT, kElasticNet>(smem, fit, prog, ra, st);
+    default: return launch_dense_variant<KT, kGroupLasso>(smem, fit, prog, ra, st);
+  }
 }
 
 int dense_kt_bucket(int K) { return K == 1 ? 1 : K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32; }
+
+// One launch per fit: the instantiation for the fit's class-count bucket (1, 4, 8, 16, 32) and penalty.
+cudaError_t launch_saga_dense(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  switch (dense_kt_bucket(K)) {
+    case 1: return launch_dense_kt<1>(pen, smem, fit, prog, ra, st);
+    case 4: return launch_dense_kt<4>(pen, smem, fit, prog, ra, st);
+    case 8: return launch_dense_kt<8>(pen, smem, fit, prog, ra, st);
+    case 16: return launch_dense_kt<16>(pen, smem, fit, prog, ra, st);
+    default: return launch_dense_kt<32>(pen, smem, fit, prog, ra, st);
+  }
+}
 
 }  // namespace sgd

@@ -189,8 +189,7 @@ __device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<u
 __device__ __forceinline__ uint32_t dep_hash2(int32_t j) { return (static_cast<uint32_t>(j) * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
 
 __global__ void __launch_bounds__(256)
-wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ prog, const RoundArgs* __restrict__ args,
-                 int window) {
+wave_deps_kernel(const FitDev* __restrict__ fit, const RoundArgs ra, int window) {
   // the index runs of the block's rows and of the `window` rows before them, staged once in shared memory: the
   // membership searches below then never leave the SM
   extern __shared__ __align__(16) unsigned char deps_smem[];
@@ -199,10 +198,9 @@ wave_deps_kernel(const FitDev* __restrict__ fits, const Progress* __restrict__ p
   uint32_t (*sbits)[kDepBitWords] = reinterpret_cast<uint32_t (*)[kDepBitWords]>(deps_smem + size_t(nslots_alloc) * kCap * 4);   // hashed membership filter per row
   int32_t* snnz = reinterpret_cast<int32_t*>(deps_smem + size_t(nslots_alloc) * (kCap + kDepBitWords) * 4);
   uint32_t* ssamp = reinterpret_cast<uint32_t*>(snnz + nslots_alloc);
-  const int fit_id = blockIdx.y;
-  const RoundArgs ra = args[fit_id];
-  if (ra.n_epochs <= 0 || prog[fit_id].status != kRunning || ra.dep == nullptr) return;
-  const FitDev& f = fits[fit_id];
+  // depends on the sampling sequence alone (not on the fit's progress), so it can run ahead of the solver
+  if (ra.n_epochs <= 0 || ra.dep == nullptr) return;
+  const FitDev& f = *fit;
   const int64_t n = f.n;
   const int64_t total = n * ra.n_epochs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -893,16 +891,20 @@ __device__ __forceinline__ int wave_role(int warp, int S) {   // -1 chain, -2 id
 
 template <int S>
 __global__ void __launch_bounds__(wave_block_warps(S) * 32, 1)
-saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const RoundArgs* __restrict__ args) {
+saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   extern __shared__ __align__(128) unsigned char wave_smem_raw[];
   WaveSmem& sm = *reinterpret_cast<WaveSmem*>(wave_smem_raw);
 
-  const int fit_id = blockIdx.x;
-  const RoundArgs ra = args[fit_id];
-  Progress& pg = prog[fit_id];
-  if (ra.n_epochs <= 0 || pg.status != kRunning) return;
+  Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (ra.n_epochs <= 0 || pg.status != kRunning) {
+    if (threadIdx.x == 0) {
+      pg.epochs_last_launch = 0;
+      publish_progress(f.mirror, pg, ra.round_id);
+    }
+    return;
+  }
   const bool free_run = (ra.flags & 1) != 0;
-  const FitDev& f = fits[fit_id];
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int role = wave_role(warp, S);
@@ -1011,6 +1013,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    publish_progress(f.mirror, pg, ra.round_id);
   }
 }
 
@@ -1018,17 +1021,21 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, 
 constexpr int kGenThreads = 256;
 
 __global__ void __launch_bounds__(kGenThreads, 1)
-saga_sparse_generic_kernel(FitDev* __restrict__ fits, Progress* __restrict__ prog, const RoundArgs* __restrict__ args) {
+saga_sparse_generic_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   __shared__ double red[2][2 * 32 * (kGenThreads / 32)];   // [parity][warp][2K]  (K <= 32)
   __shared__ double gch_s[32];
   __shared__ double cred[2 * (kGenThreads / 32)];
 
-  const int fit_id = blockIdx.x;
-  const RoundArgs ra = args[fit_id];
-  Progress& pg = prog[fit_id];
-  if (ra.n_epochs <= 0 || pg.status != kRunning) return;
+  Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (ra.n_epochs <= 0 || pg.status != kRunning) {
+    if (threadIdx.x == 0) {
+      pg.epochs_last_launch = 0;
+      publish_progress(f.mirror, pg, ra.round_id);
+    }
+    return;
+  }
   const bool free_run = (ra.flags & 1) != 0;
-  const FitDev& f = fits[fit_id];
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int K = f.K, Ky = f.Ky, p = f.p;
@@ -1202,6 +1209,7 @@ saga_sparse_generic_kernel(FitDev* __restrict__ fits, Progress* __restrict__ pro
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    publish_progress(f.mirror, pg, ra.round_id);
   }
 }
 
@@ -1216,38 +1224,36 @@ int wave_warps() {
 }
 
 template <int S>
-static cudaError_t launch_wave(int n_fits, FitDev* fits, Progress* prog, const RoundArgs* args, cudaStream_t st) {
+static cudaError_t launch_wave(FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   // per device and cheap: set on every launch (the ABI lets one process move between devices, sgdnet_set_device)
   cudaError_t e = cudaFuncSetAttribute(saga_sparse_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(sizeof(WaveSmem)));
   if (e != cudaSuccess) return e;
-  saga_sparse_wave_kernel<S><<<n_fits, wave_block_warps(S) * 32, sizeof(WaveSmem), st>>>(fits, prog, args);
+  saga_sparse_wave_kernel<S><<<1, wave_block_warps(S) * 32, sizeof(WaveSmem), st>>>(fit, prog, ra);
   return cudaGetLastError();
 }
 
-cudaError_t launch_wave_deps(int n_fits, const FitDev* fits, const Progress* prog, const RoundArgs* args,
-                             int64_t max_rows, int sms, cudaStream_t st) {
-  const int64_t want = (max_rows + kDepRows - 1) / kDepRows;
-  const int64_t cap = std::max<int64_t>(1, int64_t(sms) * 8 / std::max(1, n_fits));
-  dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min(want, cap))), n_fits);
+// `ctas`: how many CTAs this fit's conflict-code pass may use (the caller shares the GPU among the fits in flight)
+cudaError_t launch_wave_deps(const FitDev* fit, const RoundArgs& ra, int64_t rows, int ctas, cudaStream_t st) {
+  const int64_t want = (rows + kDepRows - 1) / kDepRows;
+  dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, ctas))));
   const int window = wave_warps() - 1;
   const size_t smem = size_t(kDepRows + window) * ((kCap + kDepBitWords) * 4 + 8);
   cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (e != cudaSuccess) return e;
-  wave_deps_kernel<<<grid, 256, smem, st>>>(fits, prog, args, window);
+  wave_deps_kernel<<<grid, 256, smem, st>>>(fit, ra, window);
   return cudaGetLastError();
 }
 
-cudaError_t launch_saga_sparse(int n_fits, bool fast_k1, FitDev* fits, Progress* prog, const RoundArgs* args,
-                               cudaStream_t st) {
+cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   if (fast_k1) {
     switch (wave_warps()) {
-      case 4: return launch_wave<4>(n_fits, fits, prog, args, st);
-      case 12: return launch_wave<12>(n_fits, fits, prog, args, st);
-      default: return launch_wave<8>(n_fits, fits, prog, args, st);
+      case 4: return launch_wave<4>(fit, prog, ra, st);
+      case 12: return launch_wave<12>(fit, prog, ra, st);
+      default: return launch_wave<8>(fit, prog, ra, st);
     }
   }
-  saga_sparse_generic_kernel<<<n_fits, kGenThreads, 0, st>>>(fits, prog, args);
+  saga_sparse_generic_kernel<<<1, kGenThreads, 0, st>>>(fit, prog, ra);
   return cudaGetLastError();
 }
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib.lib, n), n
-    assert lib.lib.sgdnet_abi_version() == 2
+    assert lib.lib.sgdnet_abi_version() == 3
 
 
 def test_struct_sizes_match_the_header():
@@ -51,6 +51,34 @@ def test_product_and_oracle_generators_are_the_same_stream(oracle):
     a, b = lib.rng_from_seed(2024), oracle.rng_from_seed(2024)
     np.testing.assert_array_equal(lib.unif(a, 2000), oracle.unif(b, 2000))     # crosses 3 twists of the state
     assert a.mti == b.mti and list(a.mt) == list(b.mt)
+
+
+def _check_device_schedule(lib, oracle, on_host):
+    """the block-parallel MT19937 regeneration (rng.cu) against the sequential generator: indices, the generator state
+    at every epoch boundary, and the state handed back; starting positions inside, at the end of and before a block,
+    n smaller and larger than a block of 624 words."""
+    for seed, burn, n, ne in ((1, 0, 1000, 3), (7, 5, 10, 16), (42, 623, 624, 2), (3, 624, 1247, 4), (9, 100, 50_000, 2), (11, 17, 1, 5)):
+        a, b = lib.rng_from_seed(seed), oracle.rng_from_seed(seed)
+        lib.unif(a, burn)
+        oracle.unif(b, burn)
+        seq, states = lib.rng_indices(a, n, ne, on_host=on_host)
+        want = np.empty(n * ne, dtype=np.uint32)
+        c = oracle.rng_from_seed(seed)
+        oracle.unif(c, burn)
+        for e in range(ne + 1):
+            assert states[e].mti % 624 == c.mti % 624 or (states[e].mti, c.mti) in ((624, 624),), (seed, e, states[e].mti, c.mti)
+            # same stream from here on (the state may be held before or after a pending block regeneration)
+            s_copy = _abi.Rng.from_buffer_copy(states[e])
+            c_copy = _abi.Rng.from_buffer_copy(c)
+            np.testing.assert_array_equal(lib.unif(s_copy, 700), oracle.unif(c_copy, 700))
+            if e < ne:
+                oracle.lib.oracle_draw_indices(C.byref(c), C.c_uint32(n), C.c_int64(n), want[e * n:].ctypes.data_as(C.POINTER(C.c_uint32)))
+        np.testing.assert_array_equal(seq, want)
+        np.testing.assert_array_equal(lib.unif(a, 10), oracle.unif(c, 10))     # handed back advanced by n * ne draws
+
+
+def test_device_rng_schedule_on_the_host(oracle):
+    _check_device_schedule(sg.product(), oracle, on_host=True)
 
 
 def test_bad_arguments_are_rejected_before_any_device_work():

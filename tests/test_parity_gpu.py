@@ -165,6 +165,38 @@ def test_rng_stream_is_advanced_exactly_long_warm_path(cuda, oracle):
     np.testing.assert_array_equal(oracle.unif(ro, 5), want)
 
 
+def test_device_rng_kernel_matches_the_sequential_generator(cuda, oracle):
+    """mt_indices_kernel (rng.cu): indices, per-epoch generator snapshots and the handed-back state, word for word."""
+    from test_abi_cpu import _check_device_schedule
+    _check_device_schedule(cuda, oracle, on_host=False)
+
+
+def test_batch_of_mixed_kernel_variants_and_sizes(cuda, oracle):
+    """One batch holding fits that need different solver kernels (wavefront K = 1, generic sparse for standardize = TRUE
+    and for multinomial) on row subsets of very different sizes: every fit is its own pipeline, none waits for another,
+    and each equals the oracle's fit of the same rows with the same seed."""
+    from sgdnet_b200 import api
+    x, yb = synth.binomial_sparse(3000, 200, 10, seed=77)
+    rows_small = np.arange(0, 3000, 7, dtype=np.int32)
+    rows_half = np.arange(0, 3000, 2, dtype=np.int32)
+    cases = [(None, dict(alpha=1.0, standardize=False)), (rows_small, dict(alpha=0.5, standardize=False)),
+             (rows_half, dict(alpha=0.3, standardize=True)), (rows_small, dict(alpha=0.0, standardize=False)),
+             (None, dict(alpha=0.7, standardize=True))]
+    specs, keeps = [], []
+    for k, (rows, kw) in enumerate(cases):
+        ctl, keep = api.build_control("binomial", 1, alpha=kw["alpha"], nlambda=6, lambda_min_ratio=1e-3, lambda_=None, maxit=40,
+                                      standardize=kw["standardize"], intercept=True, thresh=1e-3, standardize_response=False,
+                                      debug=False)
+        keeps.append(keep)
+        specs.append(dict(train_rows=rows, test_rows=None, control=ctl, rng=cuda.rng_from_seed(50 + k)))
+    raws, _ = cuda.fit_batch(x, yb.reshape(-1, 1), specs)
+    xr = x.tocsr()
+    for k, (rows, kw) in enumerate(cases):
+        xs, ys = (x, yb) if rows is None else (xr[rows].tocsc(), yb[rows])
+        r = sg.sgdnet(xs, ys, family="binomial", nlambda=6, lambda_min_ratio=1e-3, maxit=40, seed=50 + k, backend=oracle, **kw)
+        assert_fit_parity(raws[k], r.raw)
+
+
 def test_predict_and_score(cuda, oracle):
     x, y = _heart()
     fit = sg.sgdnet(x, y, family="binomial", alpha=0.5, standardize=False, nlambda=10, seed=1, backend=cuda)
