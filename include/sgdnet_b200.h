@@ -46,6 +46,13 @@ extern "C" {
 #define SGDNET_MULTINOMIAL   2
 #define SGDNET_MGAUSSIAN     3
 
+/* type.measure of score() (R/score.R:55-178) */
+#define SGDNET_MEASURE_DEVIANCE 0
+#define SGDNET_MEASURE_MSE      1
+#define SGDNET_MEASURE_MAE      2
+#define SGDNET_MEASURE_CLASS    3
+#define SGDNET_MEASURE_AUC      4
+
 /* The `control` list built at R/sgdnet.R:346-359 and read at src/sgdnet.cpp:76-78,129-138. */
 typedef struct sgdnet_control {
   int32_t  family;               /* control$family                                      */
@@ -184,6 +191,10 @@ typedef struct sgdnet_fit_spec {
   int32_t        lambda_from;  /* -1, or the index of an EARLIER spec of the batch whose lambda path (automatic or
                                   given) this fit uses: `lambda = lambda[[i]]` of R/cv_sgdnet.R:164, 186, known after
                                   that fit's setup, so full fits and their fold fits can share one batch      */
+  int32_t        measure;      /* SGDNET_MEASURE_*: type.measure of the held-out score (0 = deviance)          */
+  int32_t        path_only;    /* non-zero: SetupSgdnet up to the lambda path only (src/sgdnet.cpp:119-184): the
+                                  result carries `lambda` and `nulldev`, nothing is fitted. A rank of a sharded
+                                  cv_sgdnet run uses it for the alphas whose full-data fit another rank owns   */
   int32_t        pad_;
   sgdnet_control control;
   sgdnet_rng     rng;

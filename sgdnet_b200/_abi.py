@@ -92,6 +92,8 @@ class FitSpec(C.Structure):
         ("test_rows", c_int32_p),
         ("n_test", C.c_int64),
         ("lambda_from", C.c_int32),
+        ("measure", C.c_int32),
+        ("path_only", C.c_int32),
         ("pad_", C.c_int32),
         ("control", Control),
         ("rng", Rng),
@@ -342,6 +344,8 @@ class Library:
                 te = np.ascontiguousarray(te, dtype=np.int32); keep.append(te)
                 arr[i].test_rows = _ptr(te, c_int32_p); arr[i].n_test = te.size
             arr[i].lambda_from = int(s.get("lambda_from", -1))
+            arr[i].measure = int(s.get("measure", 0))
+            arr[i].path_only = int(bool(s.get("path_only", False)))
             arr[i].control = s["control"]
             arr[i].rng = s["rng"]
             n_lambda = max(n_lambda, s["control"].n_lambda)

@@ -369,10 +369,9 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
     Deviations, both documented in DESIGN.md: sparse x stays sparse (the reference densifies it,
     :130, quirk Q12), and every fit gets its own generator `set.seed(fit_seeds[k])` (default
     seed + k, full fits first) so that folds can run concurrently. `shard` (a
-    `sgdnet_b200.shard.Shard`) deals the fold fits to the ranks longest-first; one all_gather of the per-fit score
-    rows ends the run. The #alpha full-data fits run on every rank (concurrently with each other, one CTA each):
-    they supply the lambda paths every rank needs and the fit object every rank returns, and replicating them
-    costs no wall time because a fit occupies one SM.
+    `sgdnet_b200.shard.Shard`) deals ALL the fits - full-data and fold - to the ranks longest-first; one all_gather of
+    the per-fit score rows ends the run, plus a broadcast of the selected alpha's full fit from the rank that owns it.
+    `fits[i]` is None on ranks that do not own alpha i's full fit.
     """
     lib = backend or _abi.product()
     if type_measure != "deviance":
@@ -416,10 +415,17 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
     if shard is None:
         from .shard import Shard
         shard = Shard()
+    # Every fit of the call - the #alpha full-data fits and the #alpha x #folds fold fits - is dealt to the ranks
+    # longest-first by its number of training rows (R/cv_sgdnet.R:160-200 runs them one after the other). A fold fit
+    # needs its alpha's lambda path, which comes from the full fit's SETUP, not its solution (src/utils.h:157-165), so a
+    # rank that does not own an alpha's full fit asks for that setup only (`path_only`).
     plan_costs = [float(len(w["train_rows"])) for w in plan]
-    mine = shard.mine(plan_costs)
+    owned = shard.mine([float(n)] * n_full + plan_costs)
+    my_full = [k for k in owned if k < n_full]
+    mine = [k - n_full for k in owned if k >= n_full]
     cv_rows = np.full((len(plan), opts["nlambda"] if lambdas[0] is None else max(len(l) for l in lambdas)), np.nan)
     fold_fits = [None] * len(plan)
+    fits = [None] * n_full
 
     def control_for(a, lam, n_rows):
         lmr = opts["lambda_min_ratio"] if opts["lambda_min_ratio"] is not None else (0.01 if n_rows < p else 0.0001)
@@ -429,14 +435,15 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                              standardize_response=opts["standardize_response"], debug=False)
 
     if batched and lib.has("fit_batch_dense"):
-        # ONE batch: the full-data fits (they supply each alpha's lambda path, R/cv_sgdnet.R:160-164) and this rank's
-        # fold fits, which take that path through `lambda_from` - it is known after the full fit's setup, so all the
-        # fits run concurrently, one CTA each
+        # ONE batch per rank: its full-data fits (or just their lambda paths) and its fold fits, which take that path
+        # through `lambda_from` - it is known after the full fit's setup, so all the fits run concurrently, each its
+        # own pipeline on the device
         specs, keeps = [], []
         for i, a in enumerate(alphas):
             ctl, keep = control_for(a, lambdas[i], n)
             keeps.append(keep)
-            specs.append(dict(train_rows=None, test_rows=None, control=ctl, rng=lib.rng_from_seed(fit_seeds[i])))
+            specs.append(dict(train_rows=None, test_rows=None, control=ctl, rng=lib.rng_from_seed(fit_seeds[i]),
+                              path_only=i not in my_full))
         for k in mine:
             w = plan[k]
             ctl, keep = control_for(w["alpha"], lambdas[w["alpha_index"]], len(w["train_rows"]))
@@ -445,14 +452,17 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                               rng=lib.rng_from_seed(fit_seeds[n_full + k]),
                               lambda_from=w["alpha_index"] if lambdas[w["alpha_index"]] is None else -1))
         raws, scores = lib.fit_batch(x, ymat, specs)
-        fits = [wrap_fit(raw, family, a, class_names, n) for raw, a in zip(raws[:n_full], alphas)]
-        lambdas = [f.lambda_ for f in fits]
+        lambdas = [raw.lambda_.copy() for raw in raws[:n_full]]
+        for i in my_full:
+            fits[i] = wrap_fit(raws[i], family, alphas[i], class_names, n)
         for k, raw, sc in zip(mine, raws[n_full:], scores[n_full:]):
             fold_fits[k] = wrap_fit(raw, family, plan[k]["alpha"], class_names, len(plan[k]["train_rows"]))
             cv_rows[k, :len(raw.lambda_)] = sc[:len(raw.lambda_)]
     else:
+        # one call per fit (a backend without the batch entry point: the CPU oracle in the tests); unsharded full fits
         fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
                 for i, a in enumerate(alphas)]
+        my_full = list(range(n_full))
         lambdas = [f.lambda_ for f in fits]
         cv_rows = np.full((len(plan), max(len(l) for l in lambdas)), np.nan)
         yarr = np.asarray(y)
@@ -473,6 +483,9 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
         blocks.append(np.column_stack([np.full(len(lambdas[i]), a), lambdas[i], _summarize(cv_raw[i])]))
     optima = [_find_optimum(b) for b in blocks]
     best = int(np.argmin([o["error_min"] for o in optima]))
+    if shard.world > 1:            # the model the call returns lives on the rank that fitted it
+        owner = int(shard.owner_of([float(n)] * n_full + plan_costs)[best])
+        fits[best] = shard.broadcast_object(fits[best], src=owner)
     name = {"gaussian": "Mean-Squared Error", "mgaussian": "Mean-Squared Error", "binomial": "Binomial Deviance",
             "multinomial": "Multnomial Deviance"}[family]
     return CvSgdnet(alpha=alphas, lambda_=lambdas, cv_raw=cv_raw, cv_summary=np.vstack(blocks), fit=fits[best],

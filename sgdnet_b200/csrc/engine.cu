@@ -102,6 +102,16 @@ struct Arena {
     slabs.push_back(s);
     return p;
   }
+  // one slab for everything a batch is about to allocate (a cudaMalloc per fit costs milliseconds)
+  void reserve(size_t bytes) {
+    if (bytes == 0) return;
+    Slab s;
+    s.size = bytes;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, s.size));
+    s.base = static_cast<char*>(p);
+    dev.push_back(s);
+  }
   template <typename T>
   T* alloc(size_t count, bool zero = true) {
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
@@ -173,8 +183,6 @@ struct FitJob {
   bool have_handed_back = false;
   // ---- launch buffers, double buffered: [buf] is consumed by the launch in flight while [buf ^ 1] is prepared
   uint32_t* seq_dev[2] = {nullptr, nullptr};
-  uint64_t* dep_dev[2] = {nullptr, nullptr};   // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
-  uint8_t* dup_dev[2] = {nullptr, nullptr};
   MtState* snap_dev[2] = {nullptr, nullptr};   // [epochs_per_launch + 1] generator snapshots at epoch boundaries
   int epochs_per_launch = 1;
   int buf = 0;
@@ -193,12 +201,14 @@ struct FitJob {
   size_t dense_smem = 0;
   double seconds_solver = 0.0, seconds_dev = 0.0;
   uint64_t launches = 0;
+  double t_submit = 0.0;
   // ---- scoring of held-out rows after the fit (cv)
   const int32_t* test_rows = nullptr;
   int64_t n_test = 0;
   int32_t measure = 0;
   double* score_dev = nullptr;
   bool scored = false;
+  bool path_only = false;             // setup up to the lambda path only: no device state, nothing runs
 };
 
 struct Engine {
@@ -214,7 +224,7 @@ struct Engine {
   bool host_rng = std::getenv("SGDNET_HOST_RNG") != nullptr;           // draw MT indices on the host (development aid)
   bool no_overlap = std::getenv("SGDNET_NO_PREP_OVERLAP") != nullptr;  // prepare a launch only when it is due
   double seconds_setup = 0.0;
-  double t_begin = 0.0;
+  double t_begin = 0.0, t_run = 0.0;
   // raw design for scoring (device)
   DeviceDesign raw_dev;
   bool raw_uploaded = false;
@@ -298,6 +308,21 @@ struct Engine {
     return job.plan.build(d, std::move(ysub), Ky, ctl);
   }
 
+  // device bytes alloc_fit is about to carve for this job (upper estimate), so that a batch reserves them in one go
+  size_t fit_device_bytes(const FitJob& job) const {
+    const HostDesign& d = *job.design;
+    const FitPlan& pl = job.plan;
+    const size_t K = pl.K, p = d.p, L = pl.n_lambda, n = d.n;
+    const bool wave = d.sparse && K == 1 && !pl.standardize;
+    size_t epl = std::max<int64_t>(1, std::min<int64_t>(16, 200000 / std::max<int64_t>(1, d.n)));
+    if (const char* env = std::getenv("SGDNET_EPOCHS_PER_LAUNCH")) epl = std::max(1, std::atoi(env));
+    size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 32 : 0) + (d.sparse ? (n + 1) * 8 : 0);
+    b += L * p * K * 8 + L * K * 8 + L * 24 + (pl.debug ? L * size_t(pl.max_iter) * 8 : 0);
+    b += 2 * (epl * n * 4 + (epl + 1) * sizeof(MtState));
+    b += size_t(sms) * 4 * 8 + sizeof(FitDev) + sizeof(Progress) + sizeof(MtState);
+    return b + 64 * Arena::kAlign;
+  }
+
   void alloc_fit(FitJob& job) {
     const HostDesign& d = *job.design;
     const FitPlan& pl = job.plan;
@@ -359,10 +384,6 @@ struct Engine {
     const int nbuf = job.device_rng ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) {
       job.seq_dev[b] = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
-      if (job.variant == Variant::SparseK1) {
-        job.dep_dev[b] = arena.alloc<uint64_t>(size_t(epl) * d.n * 32, false);
-        job.dup_dev[b] = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
-      }
       if (job.device_rng) job.snap_dev[b] = arena.alloc<MtState>(size_t(epl) + 1, false);
     }
     if (job.device_rng) {
@@ -486,12 +507,6 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------------------------- launches of one fit
-  int deps_ctas() const {
-    int active = 0;
-    for (const FitJob& j : jobs) active += (j.phase != Phase::Done && j.phase != Phase::Parked) ? 1 : 0;
-    return std::max(8, sms * 6 / std::max(1, active));
-  }
-
   // the caller's generator -> device, at the start of run(); a launch prepared ahead stays valid when the caller hands
   // back the generator exactly as it received it
   void upload_rng(FitJob& j) {
@@ -516,7 +531,7 @@ struct Engine {
     const int ne = ne_fixed > 0 ? ne_fixed
                                 : static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(epl), std::max<uint32_t>(left, 1u)));
     const int b = j.buf;
-    RoundArgs ra{j.seq_dev[b], j.dep_dev[b], j.dup_dev[b], ne, flags, ++j.round_id, 0u};
+    RoundArgs ra{j.seq_dev[b], ne, flags, ++j.round_id, 0u};
     const int64_t n = j.dev.n;
     if (j.prepped) {
       CK(cudaStreamWaitEvent(j.st, j.ev_prep, 0));
@@ -538,12 +553,6 @@ struct Engine {
       }
       CK(cudaEventRecord(j.ev_idx, j.st));
       j.idx_on_prep = false;
-      if (j.variant == Variant::SparseK1) {
-        RoundArgs rd = ra;
-        rd.n_epochs = j.device_rng ? epl : ne;
-        CK(launch_wave_deps(j.dev_ptr, rd, n * rd.n_epochs, deps_ctas(), j.st));
-        ++j.launches;
-      }
     }
     if (j.variant != Variant::Dense) {
       CK(launch_lag_scaling(j.dev_ptr, j.prog_ptr, j.st));
@@ -557,20 +566,16 @@ struct Engine {
     ++j.launches;
     CK(cudaEventRecord(j.ev1, j.st));
     j.ne_submitted = ne;
+    j.t_submit = now_s();
     j.prepped = false;
     j.prepped_next = false;
-    // ---- the next launch's indices and conflict codes, prepared on the second stream while this one runs, on the
-    // assumption that this launch consumes all `ne` epochs (it does unless the lambda converges inside it)
+    // ---- the next launch's indices, generated on the second stream while this one runs, on the assumption that this
+    // launch consumes all `ne` epochs (it does unless the lambda converges inside it)
     if (j.device_rng && !no_overlap) {
       if (!j.idx_on_prep) CK(cudaStreamWaitEvent(j.st_prep, j.ev_idx, 0));
       const int nb = b ^ 1;
       CK(launch_mt_indices(j.snap_dev[b] + ne, static_cast<uint32_t>(n), epl, j.seq_dev[nb], j.snap_dev[nb], j.st_prep));
       ++j.launches;
-      if (j.variant == Variant::SparseK1) {
-        RoundArgs rd{j.seq_dev[nb], j.dep_dev[nb], j.dup_dev[nb], epl, 0, 0u, 0u};
-        CK(launch_wave_deps(j.dev_ptr, rd, n * epl, deps_ctas(), j.st_prep));
-        ++j.launches;
-      }
       CK(cudaEventRecord(j.ev_prep, j.st_prep));
       j.prepped_next = true;
     }
@@ -586,8 +591,9 @@ struct Engine {
     CK(cudaEventElapsedTime(&ms, j.ev0, j.ev1));
     j.seconds_solver += ms * 1e-3;
     if (trace_rounds)
-      std::fprintf(stderr, "[sgdnet_b200] fit %d: launch %u, %d epochs at lambda %d, solver %.3f ms\n",
-                   static_cast<int>(&j - jobs.data()), j.round_id, static_cast<int>(used_epochs), pg.lambda_ind, ms);
+      std::fprintf(stderr, "[sgdnet_b200] t=%9.3f ms fit %d: launch %u done (submitted t=%9.3f), %d epochs at lambda %d, solver %.3f ms%s\n",
+                   (now_s() - t_run) * 1e3, static_cast<int>(&j - jobs.data()), j.round_id, (j.t_submit - t_run) * 1e3,
+                   static_cast<int>(used_epochs), pg.lambda_ind, ms, j.idx_on_prep ? " (prepared ahead)" : "");
     if (j.device_rng) {
       j.cur_state = j.snap_dev[j.buf] + used_epochs;
       if (j.prepped_next && used_epochs == static_cast<uint64_t>(j.ne_submitted)) {
@@ -651,6 +657,7 @@ struct Engine {
   // Runs every job to the end of its path (or, with `only_lambda` >= 0, until that lambda is finished). `score`: fits
   // with held-out rows are scored on their own stream as soon as they are done.
   void run(int only_lambda = -1, bool score = false) {
+    t_run = now_s();
     for (FitJob& j : jobs) {
       if (j.phase == Phase::Parked) j.phase = Phase::Idle;
       if (j.phase != Phase::Done) upload_rng(j);
@@ -692,16 +699,18 @@ struct Engine {
       }
     }
     for (FitJob& j : jobs) {
+      if (j.path_only) continue;
       CK(cudaStreamSynchronize(j.st));
       CK(cudaStreamSynchronize(j.st_prep));
     }
+    if (trace_rounds) std::fprintf(stderr, "[sgdnet_b200] run: %.3f ms\n", (now_s() - t_run) * 1e3);
   }
 
   // ---------------------------------------------------------------------------------- results
   void fill_result(int i, sgdnet_result* out) {
     FitJob& j = jobs[i];
     const FitPlan& pl = j.plan;
-    const int L = pl.n_lambda, K = pl.K, p = j.dev.p;
+    const int L = pl.n_lambda, K = pl.K, p = j.design->p;
     std::memset(out, 0, sizeof(*out));
     out->n_lambda = L;
     out->n_classes = K;
@@ -716,13 +725,25 @@ struct Engine {
     out->losses_ptr = static_cast<int64_t*>(mal(sizeof(int64_t) * (L + 1)));
     if (!out->a0 || !out->beta || !out->lambda || !out->dev_ratio || !out->return_codes || !out->epochs || !out->losses_ptr)
       throw CudaFail{cudaErrorMemoryAllocation, "result buffers"};
+    std::memcpy(out->lambda, pl.lambda.data(), sizeof(double) * L);
+    out->nulldev = pl.nulldev;
+    if (j.path_only) {               // the lambda path and the null deviance are all there is
+      std::memset(out->a0, 0, sizeof(double) * L * K);
+      std::memset(out->beta, 0, sizeof(double) * size_t(L) * p * K);
+      std::memset(out->dev_ratio, 0, sizeof(double) * L);
+      std::memset(out->return_codes, 0, sizeof(uint32_t) * L);
+      std::memset(out->epochs, 0, sizeof(uint32_t) * L);
+      out->losses = static_cast<double*>(mal(8));
+      for (int l = 0; l <= L; ++l) out->losses_ptr[l] = 0;
+      out->seconds_setup = seconds_setup;
+      out->seconds_total = now_s() - t_begin;
+      return;
+    }
     CK(cudaMemcpy(out->a0, j.dev.a0_arch, sizeof(double) * L * K, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out->beta, j.dev.beta_arch, sizeof(double) * size_t(L) * p * K, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out->dev_ratio, j.dev.dev_ratio, sizeof(double) * L, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out->return_codes, j.dev.codes, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out->epochs, j.dev.epochs, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost));
-    std::memcpy(out->lambda, pl.lambda.data(), sizeof(double) * L);
-    out->nulldev = pl.nulldev;
     uint32_t np = 0;
     for (int l = 0; l < L; ++l) np += out->epochs[l];
     out->npasses = np;
@@ -897,8 +918,9 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
     // 1. designs (one per distinct row subset x standardize), serial
     for (int i = 0; i < n_fits; ++i) {
       sgdnet_fit_spec& s = specs[i];
-      std::string err = eng.add_fit_design(s.train_rows, s.n_train, s.control, &s.rng, s.test_rows, s.n_test, 0);
+      std::string err = eng.add_fit_design(s.train_rows, s.n_train, s.control, &s.rng, s.test_rows, s.n_test, s.measure);
       if (!err.empty()) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + err);
+      eng.jobs.back().path_only = s.path_only != 0;
     }
     // 2. plans (response statistics, lambda path, step sizes) on the host cores, independent fits concurrently; a fit
     //    that takes its path from an earlier one (`lambda = lambda[[i]]`, R/cv_sgdnet.R:164, 186) goes in a later wave
@@ -946,12 +968,19 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
     }
     pt.lap("plans (all fits)");
     // 3. device state
-    for (int i = 0; i < n_fits; ++i) eng.alloc_fit(eng.jobs[i]);
+    size_t reserve = 0;
+    for (int i = 0; i < n_fits; ++i)
+      if (!eng.jobs[i].path_only) reserve += eng.fit_device_bytes(eng.jobs[i]);
+    if (n_fits > 1) eng.arena.reserve(reserve);
+    for (int i = 0; i < n_fits; ++i) {
+      if (eng.jobs[i].path_only) eng.jobs[i].phase = Phase::Done;
+      else eng.alloc_fit(eng.jobs[i]);
+    }
     pt.lap("state alloc + upload (all fits)");
     eng.finalize_batch();
     eng.run(-1, scores != nullptr);
     for (int i = 0; i < n_fits; ++i) {
-      eng.settle_rng(eng.jobs[i]);
+      if (!eng.jobs[i].path_only) eng.settle_rng(eng.jobs[i]);
       eng.fill_result(i, &results[i]);
       FitJob& j = eng.jobs[i];
       if (scores && j.scored)

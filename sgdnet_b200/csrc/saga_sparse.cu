@@ -11,8 +11,9 @@
 //     once per nonzero per update with 256-bit accesses. The exactness argument is in the comment block below.
 //     Algorithmic HBM bytes per update: 12*nnz_row + 16 (row info) + 4 (index) + 8 (y) + 16 (gradient memory).
 //
-//  wave_deps_kernel  which features of a row are also held by one of the S-1 rows before it, from the host-drawn
-//     sampling sequence alone (so it can run ahead of the solver).
+//     A scout warp walks the ring ahead of the workers and works out, exactly, which features of a row are also held
+//     by one of the S-1 rows before it (the rows that can still be in flight): a hash table of the recent rows'
+//     features in shared memory.
 //
 //  saga_sparse_generic_kernel  any K <= 32 and/or standardize = TRUE (the reference's O(p*K) virtual-centring sweeps,
 //     src/saga-sparse.h:127-128, 276-277, reproduced as block-wide passes). Phases are separated by block barriers.
@@ -92,8 +93,10 @@ __device__ __forceinline__ bool block_converged(double mc, double ms, double* re
 //                     it up (LaggedUpdate k = t), reduce the dot product, hand it to the chain warp, and once g_change
 //                     is back do AddWeighted / LaggedUpdate(k = t+1) / AddWeighted(g_sum) and scatter. Rows in flight
 //                     overlap unless they share a feature; which of a row's features ARE touched by one of the
-//                     previous S-1 rows is computed exactly, ahead of the launch, by wave_deps_kernel from the known
-//                     sampling sequence, and only those gathers wait (fdone of the conflicting row).
+//                     previous S-1 rows is computed exactly by the scout warp (below) as soon as the row's index run
+//                     is in the ring, and only those gathers wait (fdone of the conflicting row).
+//   scout warp (1)    per row, in sequence order: looks every feature of the row up in a shared-memory hash table of
+//                     the features of the rows just before it and writes the row's conflict codes into its ring slot.
 //   producer warp (1) streams rows (index run, value run, conflict codes) into a shared-memory ring with bulk copies.
 //
 // Each element of the state still sees exactly the reference's sequence of floating point operations, in the
@@ -109,7 +112,7 @@ __device__ __forceinline__ bool block_converged(double mc, double ms, double* re
 //  - fdone[q]  completes when row q's scatter is visible in HBM (only rows behind a serial row wait for it; a
 //              conflict with an ordinary row in flight is resolved through the forwarding buffer after gok).
 //  - done[q]   like fdone but chained in row order: "done(q)" means every row <= q is complete, which bounds the rows
-//              in flight to S consecutive ones (the window wave_deps_kernel looked at).
+//              in flight to S consecutive ones (the window the scout looked at).
 //  - a row whose nonzeros do not fit a ring slot, or at which the wscale reset (src/saga-sparse.h:285-295) fires,
 //    is run serially: it waits for every earlier row, and the rows after it wait for it.
 constexpr int kWSlots = 32;     // row ring depth: S rows held by the workers + rows in flight from HBM
@@ -122,13 +125,14 @@ struct WaveSlotMeta {
   int64_t start;
   double y;
   uint32_t dup;     // distance to the most recent in-window row with the same sample (0 = none)
-  uint32_t has_code;   // the row shares a feature with a row of its window: its conflict codes were copied
+  uint32_t pad_;
 };
 
 struct __align__(128) WaveSmem {
   double val[kWSlots][kCap];
   int32_t idx[kWSlots][kCap];
-  uint64_t code[kWSlots][32];   // per lane: four 16-bit conflict entries (wave_deps_kernel)
+  uint64_t code[kWSlots][32];   // per lane: four 16-bit conflict entries (scout warp)
+  uint64_t tab[2][2048];        // scout: features of the rows of the current / previous generation of 8 rows
   double fw_w[kSeq][kCap];      // forwarding: a row's caught-up (w, g_sum) and its x values by nonzero position, for
   double fw_g[kSeq][kCap];      //   the rows that touch the same feature while it is still in flight: they redo
   double fw_x[kSeq][kCap];      //   the row's coefficient step themselves as soon as its g_change is known
@@ -136,6 +140,8 @@ struct __align__(128) WaveSmem {
   WaveSlotMeta meta[kWSlots];
   uint64_t full[kWSlots];
   uint64_t empty[kWSlots];
+  uint64_t coded[kWSlots];      // completes when the scout has written the slot's conflict codes and meta.dup
+  uint32_t samp[8];             // scout: sample ids of the last 8 rows
   uint64_t rdy[kSeq];
   uint64_t gok[kSeq];
   uint64_t fdone[kSeq];
@@ -175,125 +181,15 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
   while (!mbar_test_wait(bar, par)) __nanosleep(SGD_SLEEP_NS);
 }
 
-// ---- conflict codes: for every row instance q = epoch*n + t of the staged sequence and every nonzero position e of
-// its row, a 16-bit entry about the most recent earlier row OF THE SAME EPOCH within `window` rows that holds the same
-// feature: bits 0-3 its distance d (0 = no such row), bits 4-10 the feature's position in that row (where its
-// forwarded state sits in shared memory), bit 11 "read it from HBM instead" (that row was too long for a ring slot and
-// ran serially). Lane l of a worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
+// ---- conflict codes: for every row t of an epoch and every nonzero position e of its row, a 16-bit entry about the
+// most recent earlier row OF THE SAME EPOCH within `window` = S-1 rows that holds the same feature: bits 0-3 its
+// distance d (0 = no such row), bits 4-10 the feature's position in that row (where its forwarded state sits in shared
+// memory), bit 11 "read it from HBM instead" (that row was too long for a ring slot and ran serially). Lane l of a
+// worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
 constexpr uint32_t kCodeGlobal = 1u << 11;
-
-constexpr int kDepRows = 32;      // row instances per block iteration (4 per warp)
-constexpr int kDepMaxWindow = 15;  // distances are 4-bit
-constexpr int kDepBitWords = 256;  // 8192-bit filter per row, two hash functions: ~0.06 % false positives at 100 entries
-__device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 19; }   // 13 bits
-__device__ __forceinline__ uint32_t dep_hash2(int32_t j) { return (static_cast<uint32_t>(j) * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
-
-__global__ void __launch_bounds__(256)
-wave_deps_kernel(const FitDev* __restrict__ fit, const RoundArgs ra, int window) {
-  // the index runs of the block's rows and of the `window` rows before them, staged once in shared memory: the
-  // membership searches below then never leave the SM
-  extern __shared__ __align__(16) unsigned char deps_smem[];
-  const int nslots_alloc = kDepRows + window;
-  int32_t (*sidx)[kCap] = reinterpret_cast<int32_t (*)[kCap]>(deps_smem);
-  uint32_t (*sbits)[kDepBitWords] = reinterpret_cast<uint32_t (*)[kDepBitWords]>(deps_smem + size_t(nslots_alloc) * kCap * 4);   // hashed membership filter per row
-  int32_t* snnz = reinterpret_cast<int32_t*>(deps_smem + size_t(nslots_alloc) * (kCap + kDepBitWords) * 4);
-  uint32_t* ssamp = reinterpret_cast<uint32_t*>(snnz + nslots_alloc);
-  // depends on the sampling sequence alone (not on the fit's progress), so it can run ahead of the solver
-  if (ra.n_epochs <= 0 || ra.dep == nullptr) return;
-  const FitDev& f = *fit;
-  const int64_t n = f.n;
-  const int64_t total = n * ra.n_epochs;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int32_t* __restrict__ ci = f.ci;
-  const int nslots = kDepRows + window;
-  const int64_t n_chunks = (total + kDepRows - 1) / kDepRows;
-  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int64_t q0 = chunk * kDepRows;
-    __syncthreads();                                   // the previous iteration's searches are done
-    for (int r = warp; r < nslots; r += nwarps) {      // slot r holds row instance q0 - window + r
-      const int64_t q = q0 - window + r;
-      int32_t nnz = 0;
-      uint32_t s = 0xffffffffu;
-#pragma unroll
-      for (int wd = 0; wd < kDepBitWords / 32; ++wd) sbits[r][lane + 32 * wd] = 0u;
-      __syncwarp();
-      if (q >= 0 && q < total) {
-        s = ra.seq[q];
-        const RowInfo ri = f.rows[s];
-        nnz = ri.nnz;
-        if (nnz <= kCap) {
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            const int e = c * 32 + lane;
-            if (e < nnz) {
-              const int32_t jj = ci[ri.start + e];
-              sidx[r][e] = jj;
-              const uint32_t h1 = dep_hash1(jj), h2 = dep_hash2(jj);
-              atomicOr(&sbits[r][h1 >> 5], 1u << (h1 & 31u));
-              atomicOr(&sbits[r][h2 >> 5], 1u << (h2 & 31u));
-            }
-          }
-        }
-      }
-      if (lane == 0) {
-        snnz[r] = nnz;
-        ssamp[r] = s;
-      }
-    }
-    __syncthreads();
-    for (int rl = warp; rl < kDepRows; rl += nwarps) {
-      const int64_t q = q0 + rl;
-      if (q >= total) break;
-      const int64_t t = q % n;
-      const int me = window + rl;
-      const int32_t nnz = snnz[me];
-      const uint32_t s = ssamp[me];
-      int j[kChunks];
-      uint32_t ent[kChunks], hw[kChunks], hb[kChunks], hw2[kChunks], hb2[kChunks];
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int e = c * 32 + lane;
-        j[c] = (nnz <= kCap && e < nnz) ? sidx[me][e] : -1;
-        ent[c] = 0;
-        const uint32_t h1 = dep_hash1(j[c]), h2 = dep_hash2(j[c]);
-        hw[c] = h1 >> 5;
-        hb[c] = 1u << (h1 & 31u);
-        hw2[c] = h2 >> 5;
-        hb2[c] = 1u << (h2 & 31u);
-      }
-      uint32_t dupd = 0;
-      const int dmax = static_cast<int>(t < window ? t : window);
-      for (int d = 1; d <= dmax; ++d) {
-        const int pr = me - d;
-        if (ssamp[pr] == s && dupd == 0) dupd = static_cast<uint32_t>(d);
-        const int32_t nnz2 = snnz[pr];
-        if (nnz2 == 0) continue;
-        const int32_t* __restrict__ c2 = sidx[pr];
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          if (j[c] < 0 || ent[c] != 0) continue;
-          if (nnz2 > kCap) {
-            ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
-            continue;
-          }
-          if ((sbits[pr][hw[c]] & hb[c]) == 0u || (sbits[pr][hw2[c]] & hb2[c]) == 0u) continue;   // certainly absent
-          int lo = 0, hi = nnz2;               // first position with c2[pos] >= j[c]
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
-          }
-          if (lo < nnz2 && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
-        }
-      }
-      // most rows share nothing with their window (82 % at config 2's density): their 256 B of codes are neither
-      // written here nor copied by the solver's producer; bit 7 of dup[] says which rows have codes
-      const bool any = __any_sync(0xffffffffu, (ent[0] | ent[1] | ent[2] | ent[3]) != 0u);
-      if (any)
-        ra.dep[q * 32 + lane] = uint64_t(ent[0]) | (uint64_t(ent[1]) << 16) | (uint64_t(ent[2]) << 32) | (uint64_t(ent[3]) << 48);
-      if (lane == 0) ra.dup[q] = static_cast<uint8_t>(dupd | (any ? 0x80u : 0u));
-    }
-  }
-}
+constexpr int kTabSlots = 2048;     // per generation table: at most 8 rows x kCap features live, load <= 0.5
+constexpr int kGenRows = 8;         // rows per generation; the window is at most 7 rows, so a row's conflicts are in
+                                    // its own generation's table or the previous one's
 
 #ifdef SGD_WAVE_TRACE
 // Timeline trace (measurement build only): clock64 of eight events per row for rows [kTraceFrom, kTraceFrom + kTraceRows)
@@ -350,28 +246,24 @@ struct WaveConst {
 __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const RoundArgs& ra, int ep, uint32_t q_base,
                                            uint32_t n, int lane) {
   const uint32_t* __restrict__ eseq = ra.seq + size_t(ep) * n;
-  const uint8_t* __restrict__ edup = ra.dup + size_t(ep) * n;
-  const uint64_t* __restrict__ edep = ra.dep + size_t(ep) * n * 32;
   uint32_t t = (static_cast<uint32_t>(lane) - q_base) % kWSlots;   // q = q_base + t lands on slot `lane`
   bool have = t < n;
-  uint32_t s = 0, dv = 0;
+  uint32_t s = 0;
   RowInfo ri{};
   double y = 0.0;
   if (have) {
     s = eseq[t];
-    dv = edup[t];
     ri = f.rows[s];
     y = f.yt[s];
   }
   while (__any_sync(0xffffffffu, have)) {
     const uint32_t tn = t + kWSlots;
     const bool have_n = have && tn < n;
-    uint32_t sn = 0, dvn = 0;
+    uint32_t sn = 0;
     RowInfo rin{};
     double yn = 0.0;
     if (have_n) {
       sn = eseq[tn];
-      dvn = edup[tn];
       rin = f.rows[sn];
       yn = f.yt[sn];
     }
@@ -385,17 +277,15 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
         m.nnz = ri.nnz;
         m.start = ri.start;
         m.y = y;
-        m.dup = dv & 0x7fu;
-        m.has_code = dv >> 7;
+        m.dup = 0;          // filled in by the scout
+        m.pad_ = 0;
         sm.meta[lane] = m;
         if (ri.nnz > 0 && ri.nnz <= kCap) {
           const uint32_t bi = static_cast<uint32_t>((ri.nnz + 3) / 4) * 16u;
           const uint32_t bv = static_cast<uint32_t>((ri.nnz + 1) / 2) * 16u;
-          const uint32_t bc = m.has_code ? 256u : 0u;
-          mbar_expect_tx(&sm.full[lane], bi + bv + bc);
+          mbar_expect_tx(&sm.full[lane], bi + bv);
           bulk_g2s(sm.idx[lane], f.ci + ri.start, bi, &sm.full[lane]);
           bulk_g2s(sm.val[lane], f.cv + ri.start, bv, &sm.full[lane]);
-          if (bc) bulk_g2s(sm.code[lane], edep + size_t(t) * 32, 256u, &sm.full[lane]);
         } else {
           mbar_arrive(&sm.full[lane]);
         }
@@ -406,9 +296,101 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
     t = tn;
     have = have_n;
     s = sn;
-    dv = dvn;
     ri = rin;
     y = yn;
+  }
+}
+
+// ------------------------------------------------------------------ scout warp: conflict codes of the rows in the ring
+// Rows are taken in sequence order as their index runs land in the ring. tab[g & 1] holds the features of the rows of
+// generation g = t / 8 (key = feature id, value = row within the generation and position in the row), so a lookup in
+// the current and the previous generation's table finds the most recent earlier row that holds a feature; one probe
+// sequence both looks a feature up in the current table and leaves it there for the rows that follow. The table of
+// generation g - 2 is wiped when generation g starts; both are wiped at the start of an epoch (conflicts never cross an
+// epoch boundary: the epoch-end sweep rewrites every feature).
+__device__ __forceinline__ uint32_t scout_hash(uint32_t k) { return (k * 2654435761u) >> 21; }   // 11 bits
+
+__device__ __noinline__ void wave_scout(WaveSmem& sm, uint32_t q_base, uint32_t n, int window, int lane) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  // wipe both tables
+  for (int i = lane; i < 2 * kTabSlots; i += 32) (&sm.tab[0][0])[i] = 0ull;
+  if (lane < 8) sm.samp[lane] = 0xffffffffu;
+  __syncwarp();
+  int64_t long_t = -1;                 // most recent row of this epoch that was too long for a ring slot
+  for (uint32_t t = 0; t < n; ++t) {
+    const uint32_t q = q_base + t;
+    const int slot = static_cast<int>(q % kWSlots);
+    const uint32_t r = t % kGenRows, gen = t / kGenRows;
+    volatile uint64_t* tabc = sm.tab[gen & 1u];          // volatile: lanes read what other lanes just wrote
+    const volatile uint64_t* tabp = sm.tab[(gen & 1u) ^ 1u];
+    if (r == 0 && t != 0) {            // new generation: its table still holds generation gen - 2
+      for (int i = lane; i < kTabSlots; i += 32) tabc[i] = 0ull;
+      __syncwarp();
+    }
+    mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
+    const WaveSlotMeta m = sm.meta[slot];
+    const uint32_t wmax = t < static_cast<uint32_t>(window) ? t : static_cast<uint32_t>(window);
+    // the same sample drawn again inside the window (its gradient memory is in flight)
+    const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == m.s;
+    const uint32_t same_mask = __ballot_sync(kFull, same);
+    const uint32_t dupd = same_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(same_mask)) - 1) : 0u;
+    const uint32_t dl = (long_t >= 0 && t - static_cast<uint32_t>(long_t) <= wmax) ? t - static_cast<uint32_t>(long_t) : 0u;
+    uint64_t code = 0ull;
+    if (m.nnz <= kCap) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int e = c * 32 + lane;
+        const bool valid = e < m.nnz;
+        const uint32_t k = valid ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;
+        const uint64_t mine = (static_cast<uint64_t>(k + 1u) << 32) | (static_cast<uint64_t>(r) << 7) | static_cast<uint64_t>(e);
+        uint32_t found = 0;            // d | pos << 4
+        // ---- current generation: look up, then leave this row's entry in the slot where the probe ended
+        uint32_t h = scout_hash(k);
+        bool pending = valid;
+        while (__any_sync(kFull, pending)) {
+          const uint64_t cur = pending ? tabc[h] : 1ull;
+          const bool match = pending && static_cast<uint32_t>(cur >> 32) == k + 1u;
+          const bool claim = match || (pending && cur == 0ull);
+          if (match) found = (r - (static_cast<uint32_t>(cur >> 7) & 7u)) | ((static_cast<uint32_t>(cur) & 127u) << 4);
+          if (claim) tabc[h] = mine;
+          __syncwarp();
+          const bool won = claim && tabc[h] == mine;      // two lanes may have claimed the same empty slot
+          if (pending && !claim) h = (h + 1u) & (kTabSlots - 1);
+          pending = pending && !won;
+          __syncwarp();
+        }
+        // ---- previous generation (read only), for the features not met in the current one
+        bool look = valid && found == 0 && gen != 0;
+        h = scout_hash(k);
+        while (__any_sync(kFull, look)) {
+          const uint64_t cur = look ? tabp[h] : 0ull;
+          if (look) {
+            if (cur == 0ull) {
+              look = false;
+            } else if (static_cast<uint32_t>(cur >> 32) == k + 1u) {
+              const uint32_t d = r + kGenRows - (static_cast<uint32_t>(cur >> 7) & 7u);
+              if (d <= wmax) found = d | ((static_cast<uint32_t>(cur) & 127u) << 4);
+              look = false;
+            } else {
+              h = (h + 1u) & (kTabSlots - 1);
+            }
+          }
+        }
+        if ((found & 15u) > wmax) found = 0;              // (an earlier row of this generation outside a short window)
+        // a row that ran serially touches every feature as far as the rows behind it are concerned
+        if (valid && dl != 0 && (found == 0 || dl < (found & 15u))) found = dl | kCodeGlobal;
+        code |= static_cast<uint64_t>(found) << (16 * c);
+      }
+    } else {
+      long_t = static_cast<int64_t>(t);
+    }
+    sm.code[slot][lane] = code;
+    if (lane == 0) {
+      sm.meta[slot].dup = dupd;
+      sm.samp[t & 7u] = m.s;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.coded[slot]);
   }
 }
 
@@ -530,6 +512,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
     }
 
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
+    mbar_wait(&sm.coded[slot], (q / kWSlots) & 1u);
     TRACE(3, t);
     const WaveSlotMeta m = sm.meta[slot];
     const bool serial = reset_here || m.nnz > kCap;
@@ -541,8 +524,7 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
       bool valid[kChunks];
       double vr[kChunks], wr[kChunks], gr[kChunks];
       uint32_t lr[kChunks], dr[kChunks];   // dr: conflict entry (distance | position << 4 | kCodeGlobal)
-      const uint64_t code_raw = sm.code[slot][lane];
-      const uint64_t code = m.has_code ? code_raw : 0ull;   // stale ring contents when the row has no codes
+      const uint64_t code = sm.code[slot][lane];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int e = c * 32 + lane;
@@ -881,13 +863,24 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
 // critical path of the whole fit, so it gets a scheduler to itself: it is warp 3 and the other warps of that
 // sub-partition (7, 11, ...) are idle placeholders that only take part in the block barriers and the epoch-end
 // sweep (measured: 648 -> 634 cycles per update on config 2's shape, 565 -> 539 without row conflicts).
-// Role index r = rank among the remaining warps: r < S workers, r == S the producer.
-constexpr int wave_block_warps(int S) { return (S + 1) + (S + 1 + 2) / 3; }   // S+1 role warps on 3 of every 4 ids
+// Role index r = rank among the remaining warps: r < S workers, r == S the producer. The scout (role S + 1) is warp 7,
+// the second warp of the chain's sub-partition: a block of 12 warps leaves every thread the 168 registers the worker
+// needs (a 13th warp costs the workers spills); -DSGD_SCOUT_OWN_WARP puts it on a sub-partition of the workers instead.
+#ifdef SGD_SCOUT_OWN_WARP
+constexpr int wave_block_warps(int S) { return (S + 2) + (S + 2 - 1) / 3; }   // S+2 role warps on 3 of every 4 ids
 __device__ __forceinline__ int wave_role(int warp, int S) {   // -1 chain, -2 idle, else role index
   if ((warp & 3) == 3) return warp == 3 ? -1 : -2;
   const int r = warp - (warp >> 2);
+  return r <= S + 1 ? r : -2;
+}
+#else
+constexpr int wave_block_warps(int S) { return (S + 1) + (S + 1 + 2) / 3 < 8 ? 8 : (S + 1) + (S + 1 + 2) / 3; }
+__device__ __forceinline__ int wave_role(int warp, int S) {   // -1 chain, -2 idle, else role index
+  if ((warp & 3) == 3) return warp == 3 ? -1 : (warp == 7 ? S + 1 : -2);
+  const int r = warp - (warp >> 2);
   return r <= S ? r : -2;
 }
+#endif
 
 template <int S>
 __global__ void __launch_bounds__(wave_block_warps(S) * 32, 1)
@@ -931,6 +924,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
     for (int i = 0; i < kWSlots; ++i) {
       mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
+      mbar_init(&sm.coded[i], 1);
     }
     for (int i = 0; i < kSeq; ++i) {
       mbar_init(&sm.rdy[i], 1);
@@ -951,6 +945,8 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep, q_base += n) {
     if (role == S) {
       wave_producer(sm, f, ra, ep, q_base, n, lane);
+    } else if (role == S + 1) {
+      wave_scout(sm, q_base, n, S - 1, lane);
     } else if (role == -2) {
       // idle placeholder of the chain warp's scheduler
     } else if (role == -1) {
@@ -1218,7 +1214,7 @@ int wave_warps() {
   static int s = [] {
     int v = 8;
     if (const char* env = std::getenv("SGDNET_WAVE_WARPS")) v = std::atoi(env);
-    return (v == 4 || v == 8 || v == 12) ? v : 8;
+    return (v == 4 || v == 8) ? v : 8;     // the scout's tables cover a window of at most 7 rows
   }();
   return s;
 }
@@ -1233,23 +1229,10 @@ static cudaError_t launch_wave(FitDev* fit, Progress* prog, const RoundArgs& ra,
   return cudaGetLastError();
 }
 
-// `ctas`: how many CTAs this fit's conflict-code pass may use (the caller shares the GPU among the fits in flight)
-cudaError_t launch_wave_deps(const FitDev* fit, const RoundArgs& ra, int64_t rows, int ctas, cudaStream_t st) {
-  const int64_t want = (rows + kDepRows - 1) / kDepRows;
-  dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, ctas))));
-  const int window = wave_warps() - 1;
-  const size_t smem = size_t(kDepRows + window) * ((kCap + kDepBitWords) * 4 + 8);
-  cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (e != cudaSuccess) return e;
-  wave_deps_kernel<<<grid, 256, smem, st>>>(fit, ra, window);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   if (fast_k1) {
     switch (wave_warps()) {
       case 4: return launch_wave<4>(fit, prog, ra, st);
-      case 12: return launch_wave<12>(fit, prog, ra, st);
       default: return launch_wave<8>(fit, prog, ra, st);
     }
   }
