@@ -310,84 +310,126 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
 // epoch boundary: the epoch-end sweep rewrites every feature).
 __device__ __forceinline__ uint32_t scout_hash(uint32_t k) { return (k * 2654435761u) >> 21; }   // 11 bits
 
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64_if(bool pred, uint32_t a, uint64_t v) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pp;\n"
+      "setp.ne.b32 pp, %2, 0;\n"
+      "@pp st.shared.u64 [%0], %1;\n"
+      "}\n" ::"r"(a),
+      "l"(v), "r"(static_cast<int>(pred))
+      : "memory");
+}
+
+// Straight-line, predicated code inside the probe loops (a lone warp pays dearly for divergence, see above): the four
+// positions a lane owns (e = lane, lane + 32, ...) are probed together, so one loop iteration is four independent
+// shared-memory round trips, and the only convergence points are the two warp-wide ones per iteration.
 __device__ __noinline__ void wave_scout(WaveSmem& sm, uint32_t q_base, uint32_t n, int window, int lane) {
   constexpr uint32_t kFull = 0xffffffffu;
-  // wipe both tables
   for (int i = lane; i < 2 * kTabSlots; i += 32) (&sm.tab[0][0])[i] = 0ull;
   if (lane < 8) sm.samp[lane] = 0xffffffffu;
   __syncwarp();
-  int64_t long_t = -1;                 // most recent row of this epoch that was too long for a ring slot
+  const uint32_t a_tab = smem_u32(&sm.tab[0][0]);
+  uint32_t long_t = 0xffffffffu;       // most recent row of this epoch that was too long for a ring slot (none yet)
   for (uint32_t t = 0; t < n; ++t) {
     const uint32_t q = q_base + t;
     const int slot = static_cast<int>(q % kWSlots);
     const uint32_t r = t % kGenRows, gen = t / kGenRows;
-    volatile uint64_t* tabc = sm.tab[gen & 1u];          // volatile: lanes read what other lanes just wrote
-    const volatile uint64_t* tabp = sm.tab[(gen & 1u) ^ 1u];
+    const uint32_t a_cur = a_tab + (gen & 1u) * (kTabSlots * 8u), a_prev = a_tab + ((gen & 1u) ^ 1u) * (kTabSlots * 8u);
     if (r == 0 && t != 0) {            // new generation: its table still holds generation gen - 2
-      for (int i = lane; i < kTabSlots; i += 32) tabc[i] = 0ull;
+      for (int i = lane; i < kTabSlots; i += 32) sm.tab[gen & 1u][i] = 0ull;
       __syncwarp();
     }
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
-    const WaveSlotMeta m = sm.meta[slot];
+    const uint32_t s_row = sm.meta[slot].s;
+    const int nnz = sm.meta[slot].nnz;
     const uint32_t wmax = t < static_cast<uint32_t>(window) ? t : static_cast<uint32_t>(window);
     // the same sample drawn again inside the window (its gradient memory is in flight)
-    const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == m.s;
+    const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == s_row;
     const uint32_t same_mask = __ballot_sync(kFull, same);
     const uint32_t dupd = same_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(same_mask)) - 1) : 0u;
-    const uint32_t dl = (long_t >= 0 && t - static_cast<uint32_t>(long_t) <= wmax) ? t - static_cast<uint32_t>(long_t) : 0u;
-    uint64_t code = 0ull;
-    if (m.nnz <= kCap) {
+    const bool has_long = long_t != 0xffffffffu && t - long_t <= wmax;
+    const uint32_t dl = has_long ? t - long_t : 0u;
+    const bool is_long = nnz > kCap;
+    uint32_t k1[kChunks], h[kChunks], found[kChunks];
+    uint64_t mine[kChunks];
+    uint32_t pend = 0;                 // bit c: position c * 32 + lane still has to be placed in the current table
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int e = c * 32 + lane;
+      const bool valid = !is_long && e < nnz;
+      const uint32_t k = valid ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;
+      k1[c] = k + 1u;
+      h[c] = scout_hash(k);
+      mine[c] = (static_cast<uint64_t>(k + 1u) << 32) | (static_cast<uint64_t>(r) << 7) | static_cast<uint64_t>(e);
+      found[c] = 0;
+      pend |= valid ? (1u << c) : 0u;
+    }
+    const uint32_t valid_bits = pend;
+    // ---- current generation: look up, and leave this row's entry in the slot where the probe ended
+    while (__any_sync(kFull, pend != 0)) {
+      uint64_t cur[kChunks];
+      bool claim[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) cur[c] = lds_u64(a_cur + h[c] * 8u);
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        const int e = c * 32 + lane;
-        const bool valid = e < m.nnz;
-        const uint32_t k = valid ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;
-        const uint64_t mine = (static_cast<uint64_t>(k + 1u) << 32) | (static_cast<uint64_t>(r) << 7) | static_cast<uint64_t>(e);
-        uint32_t found = 0;            // d | pos << 4
-        // ---- current generation: look up, then leave this row's entry in the slot where the probe ended
-        uint32_t h = scout_hash(k);
-        bool pending = valid;
-        while (__any_sync(kFull, pending)) {
-          const uint64_t cur = pending ? tabc[h] : 1ull;
-          const bool match = pending && static_cast<uint32_t>(cur >> 32) == k + 1u;
-          const bool claim = match || (pending && cur == 0ull);
-          if (match) found = (r - (static_cast<uint32_t>(cur >> 7) & 7u)) | ((static_cast<uint32_t>(cur) & 127u) << 4);
-          if (claim) tabc[h] = mine;
-          __syncwarp();
-          const bool won = claim && tabc[h] == mine;      // two lanes may have claimed the same empty slot
-          if (pending && !claim) h = (h + 1u) & (kTabSlots - 1);
-          pending = pending && !won;
-          __syncwarp();
-        }
-        // ---- previous generation (read only), for the features not met in the current one
-        bool look = valid && found == 0 && gen != 0;
-        h = scout_hash(k);
-        while (__any_sync(kFull, look)) {
-          const uint64_t cur = look ? tabp[h] : 0ull;
-          if (look) {
-            if (cur == 0ull) {
-              look = false;
-            } else if (static_cast<uint32_t>(cur >> 32) == k + 1u) {
-              const uint32_t d = r + kGenRows - (static_cast<uint32_t>(cur >> 7) & 7u);
-              if (d <= wmax) found = d | ((static_cast<uint32_t>(cur) & 127u) << 4);
-              look = false;
-            } else {
-              h = (h + 1u) & (kTabSlots - 1);
-            }
-          }
-        }
-        if ((found & 15u) > wmax) found = 0;              // (an earlier row of this generation outside a short window)
-        // a row that ran serially touches every feature as far as the rows behind it are concerned
-        if (valid && dl != 0 && (found == 0 || dl < (found & 15u))) found = dl | kCodeGlobal;
-        code |= static_cast<uint64_t>(found) << (16 * c);
+        const bool p_c = (pend >> c) & 1u;
+        const bool match = p_c && static_cast<uint32_t>(cur[c] >> 32) == k1[c];
+        claim[c] = match || (p_c && cur[c] == 0ull);
+        const uint32_t f_c = (r - (static_cast<uint32_t>(cur[c] >> 7) & 7u)) | ((static_cast<uint32_t>(cur[c]) & 127u) << 4);
+        found[c] = match ? f_c : found[c];
+        sts_u64_if(claim[c], a_cur + h[c] * 8u, mine[c]);
       }
-    } else {
-      long_t = static_cast<int64_t>(t);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const uint64_t back = lds_u64(a_cur + h[c] * 8u);
+        const bool p_c = (pend >> c) & 1u;
+        const bool won = claim[c] && back == mine[c];      // two positions may have claimed the same empty slot
+        h[c] = (p_c && !claim[c]) ? ((h[c] + 1u) & (kTabSlots - 1)) : h[c];
+        pend &= won ? ~(1u << c) : ~0u;
+      }
     }
+    // ---- previous generation (read only), for the features not met in the current one
+    uint32_t look = 0;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      look |= (((valid_bits >> c) & 1u) && found[c] == 0 && gen != 0) ? (1u << c) : 0u;
+      h[c] = scout_hash(k1[c] - 1u);
+    }
+    while (__any_sync(kFull, look != 0)) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const uint64_t cur = lds_u64(a_prev + h[c] * 8u);
+        const bool l_c = (look >> c) & 1u;
+        const bool match = l_c && static_cast<uint32_t>(cur >> 32) == k1[c];
+        const bool stop = match || cur == 0ull;
+        const uint32_t d = r + kGenRows - (static_cast<uint32_t>(cur >> 7) & 7u);
+        found[c] = (match && d <= wmax) ? (d | ((static_cast<uint32_t>(cur) & 127u) << 4)) : found[c];
+        h[c] = (h[c] + 1u) & (kTabSlots - 1);
+        look &= stop ? ~(1u << c) : ~0u;
+      }
+    }
+    uint64_t code = 0ull;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      uint32_t f_c = ((found[c] & 15u) > wmax) ? 0u : found[c];   // an earlier row of this generation outside a short window
+      // a row that ran serially touches every feature as far as the rows behind it are concerned
+      const bool use_long = ((valid_bits >> c) & 1u) && has_long && (f_c == 0 || dl < (f_c & 15u));
+      f_c = use_long ? (dl | kCodeGlobal) : f_c;
+      code |= static_cast<uint64_t>(f_c) << (16 * c);
+    }
+    long_t = is_long ? t : long_t;
     sm.code[slot][lane] = code;
     if (lane == 0) {
       sm.meta[slot].dup = dupd;
-      sm.samp[t & 7u] = m.s;
+      sm.samp[t & 7u] = s_row;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.coded[slot]);
