@@ -61,6 +61,8 @@ struct FitDev {
   double *W, *gsum, *Wprev, *b, *gsi, *gmem;   // gmem [n][K]
   uint32_t* lag;             // [p]
   FeatState* st;             // [p] sparse K == 1: packed {W, gsum, lag} (then W mirrors st.w at epoch ends only)
+  uint64_t* last_row;        // [p] sparse K == 1: scout's table, (t + 1) << 32 | position for the last row of the epoch
+                             //     that holds the feature, 0 = none yet (wiped by the epoch-end sweep)
   double*   lag_scaling;     // [n+1] (unused when ls_identity)
   // ---- path
   const double *gamma, *alpha, *beta;   // per lambda
@@ -91,11 +93,17 @@ struct Progress {
   uint32_t epochs_last_launch;
   uint32_t round_seen;       // id of the last round (RoundArgs::round_id) whose result this is; the host polls it
   double   wscale;           // carried only inside an epoch; 1.0 between epochs
+  uint64_t solver_ns;        // device time spent in the SAGA epoch kernels so far (%globaltimer around each launch)
 };
 
 // The host does not synchronise streams to learn that a round is over: the one thread that updates a fit's Progress
 // copies it to pinned host memory, payload first, then (system-scope fence in between) the round id the host is
 // polling for. Stream order still governs everything on the device.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void publish_progress(Progress* mirror, const Progress& pg, uint32_t round_id) {
   if (mirror == nullptr) return;
   volatile Progress* m = mirror;
@@ -105,6 +113,7 @@ __device__ __forceinline__ void publish_progress(Progress* mirror, const Progres
   m->npasses = pg.npasses;
   m->epochs_last_launch = pg.epochs_last_launch;
   m->wscale = pg.wscale;
+  m->solver_ns = pg.solver_ns;
   __threadfence_system();
   m->round_seen = round_id;
 }

@@ -201,7 +201,8 @@ struct FitJob {
   size_t dense_smem = 0;
   double seconds_solver = 0.0, seconds_dev = 0.0;
   uint64_t launches = 0;
-  double t_submit = 0.0;
+  double t_submit = 0.0, t_finish = 0.0;
+  uint64_t solver_ns_seen = 0;
   // ---- scoring of held-out rows after the fit (cv)
   const int32_t* test_rows = nullptr;
   int64_t n_test = 0;
@@ -316,7 +317,7 @@ struct Engine {
     const bool wave = d.sparse && K == 1 && !pl.standardize;
     size_t epl = std::max<int64_t>(1, std::min<int64_t>(16, 200000 / std::max<int64_t>(1, d.n)));
     if (const char* env = std::getenv("SGDNET_EPOCHS_PER_LAUNCH")) epl = std::max(1, std::atoi(env));
-    size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 32 : 0) + (d.sparse ? (n + 1) * 8 : 0);
+    size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 40 : 0) + (d.sparse ? (n + 1) * 8 : 0);
     b += L * p * K * 8 + L * K * 8 + L * 24 + (pl.debug ? L * size_t(pl.max_iter) * 8 : 0);
     b += 2 * (epl * n * 4 + (epl + 1) * sizeof(MtState));
     b += size_t(sms) * 4 * 8 + sizeof(FitDev) + sizeof(Progress) + sizeof(MtState);
@@ -353,6 +354,7 @@ struct Engine {
     f.lag = arena.alloc<uint32_t>(p);
     job.variant = !d.sparse ? Variant::Dense : ((K == 1 && !f.standardize) ? Variant::SparseK1 : Variant::SparseGeneric);
     f.st = (job.variant == Variant::SparseK1) ? arena.alloc<FeatState>(p) : nullptr;
+    f.last_row = (job.variant == Variant::SparseK1) ? arena.alloc<uint64_t>(p) : nullptr;
     f.lag_scaling = d.sparse ? arena.alloc<double>(size_t(d.n) + 1, false) : nullptr;
     f.gamma = arena.upload(pl.gamma);
     f.alpha = arena.upload(pl.alpha);
@@ -433,7 +435,10 @@ struct Engine {
   }
 
   void finalize_batch() {
-    CK(cudaStreamSynchronize(stream));     // zero fills of the state (ordered on `stream`) precede every fit's stream
+    // Everything uploaded so far went through cudaMemcpy from pageable memory, which may return while the DMA into
+    // device memory is still in flight, on the legacy default stream - and the fits' streams are non-blocking, so
+    // nothing orders their kernels behind it. Zero fills are ordered on `stream`. One device-wide wait covers both.
+    CK(cudaDeviceSynchronize());
     seconds_setup = now_s() - t_begin;
   }
 
@@ -558,13 +563,17 @@ struct Engine {
       CK(launch_lag_scaling(j.dev_ptr, j.prog_ptr, j.st));
       ++j.launches;
     }
-    CK(cudaEventRecord(j.ev0, j.st));
+    // CUDA events bracket the solver only when the fit has the GPU to itself (single fits, the stepping interface): an
+    // event recorded behind a long kernel holds up the hardware queue its stream shares with other fits' streams (at
+    // most 32 queues), which caps how many fits of a batch run at once. Batches use the kernels' own %globaltimer
+    // brackets (Progress::solver_ns).
+    if (use_events()) CK(cudaEventRecord(j.ev0, j.st));
     if (j.variant == Variant::Dense)
       CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else
       CK(launch_saga_sparse(j.variant == Variant::SparseK1, j.dev_ptr, j.prog_ptr, ra, j.st));
     ++j.launches;
-    CK(cudaEventRecord(j.ev1, j.st));
+    if (use_events()) CK(cudaEventRecord(j.ev1, j.st));
     j.ne_submitted = ne;
     j.t_submit = now_s();
     j.prepped = false;
@@ -586,9 +595,12 @@ struct Engine {
     const Progress pg = *j.mirror;
     const uint64_t used_epochs = pg.epochs_last_launch;
     const uint64_t used = used_epochs * uint64_t(j.dev.n);
-    CK(cudaEventSynchronize(j.ev1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, j.ev0, j.ev1));
+    float ms = static_cast<float>((pg.solver_ns - j.solver_ns_seen) * 1e-6);
+    j.solver_ns_seen = pg.solver_ns;
+    if (use_events()) {
+      CK(cudaEventSynchronize(j.ev1));
+      CK(cudaEventElapsedTime(&ms, j.ev0, j.ev1));
+    }
     j.seconds_solver += ms * 1e-3;
     if (trace_rounds)
       std::fprintf(stderr, "[sgdnet_b200] t=%9.3f ms fit %d: launch %u done (submitted t=%9.3f), %d epochs at lambda %d, solver %.3f ms%s\n",
@@ -612,25 +624,29 @@ struct Engine {
 
   void submit_finish(FitJob& j) {
     ++j.round_id;
-    CK(cudaEventRecord(j.ev_f0, j.st));
+    j.t_finish = now_s();
+    if (use_events()) CK(cudaEventRecord(j.ev_f0, j.st));
     if (j.dev.debug) {
       CK(launch_epoch_loss(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.st));
       j.launches += 2;
     }
     CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.round_id, j.st));
     j.launches += 2;
-    CK(cudaEventRecord(j.ev_f1, j.st));
+    if (use_events()) CK(cudaEventRecord(j.ev_f1, j.st));
     j.phase = Phase::Finish;
   }
 
   void finish_done(FitJob& j) {
-    CK(cudaEventSynchronize(j.ev_f1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, j.ev_f0, j.ev_f1));
+    float ms = static_cast<float>((now_s() - j.t_finish) * 1e3);      // batches: host clock from submission to publication
+    if (use_events()) {
+      CK(cudaEventSynchronize(j.ev_f1));
+      CK(cudaEventElapsedTime(&ms, j.ev_f0, j.ev_f1));
+    }
     j.seconds_dev += ms * 1e-3;
     j.needs_finish = false;
   }
 
+  bool use_events() const { return jobs.size() == 1; }
   uint64_t idle_sweeps = 0;
   void wait_round(FitJob& j) {
     uint64_t spins = 0;
@@ -812,12 +828,23 @@ struct Engine {
   }
 
   // score(fit, x_test, y_test) of a finished fit, on the fit's own stream (R/cv_sgdnet.R:197-198)
-  void submit_score(FitJob& j) {
-    int32_t*& td = test_dev[j.test_rows];
-    if (!td) {
-      td = arena.alloc<int32_t>(j.n_test, false);
-      CK(cudaMemcpy(td, j.test_rows, sizeof(int32_t) * j.n_test, cudaMemcpyHostToDevice));
+  // held-out rows and the raw design / response on the device, before the batch starts (see finalize_batch)
+  void upload_for_scoring() {
+    bool any = false;
+    for (FitJob& j : jobs) {
+      if (j.path_only || !j.test_rows || j.n_test <= 0) continue;
+      any = true;
+      int32_t*& td = test_dev[j.test_rows];
+      if (!td) {
+        td = arena.alloc<int32_t>(j.n_test, false);
+        CK(cudaMemcpy(td, j.test_rows, sizeof(int32_t) * j.n_test, cudaMemcpyHostToDevice));
+      }
     }
+    if (any) upload_raw();
+  }
+
+  void submit_score(FitJob& j) {
+    int32_t* td = test_dev[j.test_rows];
     const int L = j.plan.n_lambda;
     j.score_dev = arena.alloc<double>(L, false);
     j.launches += predict_score(j.plan.family, j.plan.K, L, td, j.n_test, j.dev.a0_arch, j.dev.beta_arch, true, nullptr,
@@ -977,6 +1004,7 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
       else eng.alloc_fit(eng.jobs[i]);
     }
     pt.lap("state alloc + upload (all fits)");
+    if (scores) eng.upload_for_scoring();
     eng.finalize_batch();
     eng.run(-1, scores != nullptr);
     for (int i = 0; i < n_fits; ++i) {
@@ -1003,6 +1031,8 @@ int predict_or_score(const XArg& xa, const double* y, int32_t y_cols, int32_t fa
     double* bd = eng.arena.upload(bv);
     double* link_dev = link ? eng.arena.alloc<double>(size_t(L) * K * xa.n, false) : nullptr;
     double* score_dev = score ? eng.arena.alloc<double>(L) : nullptr;
+    eng.upload_raw();
+    CK(cudaDeviceSynchronize());      // pageable uploads above (see finalize_batch)
     eng.predict_score(family, K, L, nullptr, xa.n, a0d, bd, score != nullptr, link_dev, score_dev, eng.stream);
     CK(cudaStreamSynchronize(eng.stream));
     if (link) CK(cudaMemcpy(link, link_dev, sizeof(double) * size_t(L) * K * xa.n, cudaMemcpyDeviceToHost));

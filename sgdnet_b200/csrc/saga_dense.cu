@@ -82,6 +82,7 @@ saga_dense_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const R
     return;
   }
   const bool free_run = (ra.flags & 1) != 0;
+  const uint64_t t_start = globaltimer_ns();
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int K = kScalar ? 1 : f.K, p = f.p, ld = f.ld, Ky = f.Ky;
@@ -382,6 +383,7 @@ saga_dense_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const R
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    pg.solver_ns += globaltimer_ns() - t_start;
     publish_progress(f.mirror, pg, ra.round_id);
   }
 }

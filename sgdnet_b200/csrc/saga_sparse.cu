@@ -132,7 +132,6 @@ struct __align__(128) WaveSmem {
   double val[kWSlots][kCap];
   int32_t idx[kWSlots][kCap];
   uint64_t code[kWSlots][32];   // per lane: four 16-bit conflict entries (scout warp)
-  uint64_t tab[2][2048];        // scout: features of the rows of the current / previous generation of 8 rows
   double fw_w[kSeq][kCap];      // forwarding: a row's caught-up (w, g_sum) and its x values by nonzero position, for
   double fw_g[kSeq][kCap];      //   the rows that touch the same feature while it is still in flight: they redo
   double fw_x[kSeq][kCap];      //   the row's coefficient step themselves as soon as its g_change is known
@@ -187,9 +186,6 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 // memory), bit 11 "read it from HBM instead" (that row was too long for a ring slot and ran serially). Lane l of a
 // worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
 constexpr uint32_t kCodeGlobal = 1u << 11;
-constexpr int kTabSlots = 2048;     // per generation table: at most 8 rows x kCap features live, load <= 0.5
-constexpr int kGenRows = 8;         // rows per generation; the window is at most 7 rows, so a row's conflicts are in
-                                    // its own generation's table or the previous one's
 
 #ifdef SGD_WAVE_TRACE
 // Timeline trace (measurement build only): clock64 of eight events per row for rows [kTraceFrom, kTraceFrom + kTraceRows)
@@ -302,52 +298,58 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
 }
 
 // ------------------------------------------------------------------ scout warp: conflict codes of the rows in the ring
-// Rows are taken in sequence order as their index runs land in the ring. tab[g & 1] holds the features of the rows of
-// generation g = t / 8 (key = feature id, value = row within the generation and position in the row), so a lookup in
-// the current and the previous generation's table finds the most recent earlier row that holds a feature; one probe
-// sequence both looks a feature up in the current table and leaves it there for the rows that follow. The table of
-// generation g - 2 is wiped when generation g starts; both are wiped at the start of an epoch (conflicts never cross an
-// epoch boundary: the epoch-end sweep rewrites every feature).
-__device__ __forceinline__ uint32_t scout_hash(uint32_t k) { return (k * 2654435761u) >> 21; }   // 11 bits
-
-__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+// Rows are taken in sequence order as their index runs land in the ring. last_row[j] (one 64-bit word per feature, L2
+// resident like the coefficient records) names the last row of this epoch that holds feature j and the feature's
+// position in it; per row the scout gathers the words of the row's features, derives the conflict codes from them
+// (distance = t - that row, if within the window) and scatters the row's own (t, position). A row's gather has to see
+// the scatter of the row before it: same warp, __syncwarp in between, L2-only accesses (.cg). Everything is straight
+// line: four independent loads and four predicated stores per lane and row. The table is wiped by the epoch-end
+// sweep (conflicts never cross an epoch boundary: that sweep rewrites every coefficient record).
+__device__ __forceinline__ uint64_t ldcg_u64(const uint64_t* p) {
   uint64_t v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void sts_u64_if(bool pred, uint32_t a, uint64_t v) {
+__device__ __forceinline__ void stcg_u64_if(bool pred, uint64_t* p, uint64_t v) {
   asm volatile(
       "{\n"
       ".reg .pred pp;\n"
       "setp.ne.b32 pp, %2, 0;\n"
-      "@pp st.shared.u64 [%0], %1;\n"
-      "}\n" ::"r"(a),
+      "@pp st.global.cg.u64 [%0], %1;\n"
+      "}\n" ::"l"(p),
       "l"(v), "r"(static_cast<int>(pred))
       : "memory");
 }
 
-// Straight-line, predicated code inside the probe loops (a lone warp pays dearly for divergence, see above): the four
-// positions a lane owns (e = lane, lane + 32, ...) are probed together, so one loop iteration is four independent
-// shared-memory round trips, and the only convergence points are the two warp-wide ones per iteration.
-__device__ __noinline__ void wave_scout(WaveSmem& sm, uint32_t q_base, uint32_t n, int window, int lane) {
+__device__ __noinline__ void wave_scout(WaveSmem& sm, uint64_t* __restrict__ last_row, uint32_t q_base, uint32_t n,
+                                        int window, int lane) {
   constexpr uint32_t kFull = 0xffffffffu;
-  for (int i = lane; i < 2 * kTabSlots; i += 32) (&sm.tab[0][0])[i] = 0ull;
   if (lane < 8) sm.samp[lane] = 0xffffffffu;
   __syncwarp();
-  const uint32_t a_tab = smem_u32(&sm.tab[0][0]);
   uint32_t long_t = 0xffffffffu;       // most recent row of this epoch that was too long for a ring slot (none yet)
   for (uint32_t t = 0; t < n; ++t) {
     const uint32_t q = q_base + t;
     const int slot = static_cast<int>(q % kWSlots);
-    const uint32_t r = t % kGenRows, gen = t / kGenRows;
-    const uint32_t a_cur = a_tab + (gen & 1u) * (kTabSlots * 8u), a_prev = a_tab + ((gen & 1u) ^ 1u) * (kTabSlots * 8u);
-    if (r == 0 && t != 0) {            // new generation: its table still holds generation gen - 2
-      for (int i = lane; i < kTabSlots; i += 32) sm.tab[gen & 1u][i] = 0ull;
-      __syncwarp();
-    }
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
     const uint32_t s_row = sm.meta[slot].s;
     const int nnz = sm.meta[slot].nnz;
+    const bool is_long = nnz > kCap;
+    // ---- gather the table words of the row's features, then leave this row's (t, position) in their place
+    uint64_t cur[kChunks];
+    bool valid[kChunks];
+    uint32_t k[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int e = c * 32 + lane;
+      valid[c] = !is_long && e < nnz;
+      k[c] = valid[c] ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;     // clamped: invalid positions read word 0
+    }
+    __syncwarp();                      // the previous row's scatter (every lane's) precedes this row's gather
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) cur[c] = ldcg_u64(last_row + k[c]);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+      stcg_u64_if(valid[c], last_row + k[c], (static_cast<uint64_t>(t + 1u) << 32) | static_cast<uint64_t>(c * 32 + lane));
     const uint32_t wmax = t < static_cast<uint32_t>(window) ? t : static_cast<uint32_t>(window);
     // the same sample drawn again inside the window (its gradient memory is in flight)
     const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == s_row;
@@ -355,73 +357,14 @@ __device__ __noinline__ void wave_scout(WaveSmem& sm, uint32_t q_base, uint32_t 
     const uint32_t dupd = same_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(same_mask)) - 1) : 0u;
     const bool has_long = long_t != 0xffffffffu && t - long_t <= wmax;
     const uint32_t dl = has_long ? t - long_t : 0u;
-    const bool is_long = nnz > kCap;
-    uint32_t k1[kChunks], h[kChunks], found[kChunks];
-    uint64_t mine[kChunks];
-    uint32_t pend = 0;                 // bit c: position c * 32 + lane still has to be placed in the current table
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      const int e = c * 32 + lane;
-      const bool valid = !is_long && e < nnz;
-      const uint32_t k = valid ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;
-      k1[c] = k + 1u;
-      h[c] = scout_hash(k);
-      mine[c] = (static_cast<uint64_t>(k + 1u) << 32) | (static_cast<uint64_t>(r) << 7) | static_cast<uint64_t>(e);
-      found[c] = 0;
-      pend |= valid ? (1u << c) : 0u;
-    }
-    const uint32_t valid_bits = pend;
-    // ---- current generation: look up, and leave this row's entry in the slot where the probe ended
-    while (__any_sync(kFull, pend != 0)) {
-      uint64_t cur[kChunks];
-      bool claim[kChunks];
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) cur[c] = lds_u64(a_cur + h[c] * 8u);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const bool p_c = (pend >> c) & 1u;
-        const bool match = p_c && static_cast<uint32_t>(cur[c] >> 32) == k1[c];
-        claim[c] = match || (p_c && cur[c] == 0ull);
-        const uint32_t f_c = (r - (static_cast<uint32_t>(cur[c] >> 7) & 7u)) | ((static_cast<uint32_t>(cur[c]) & 127u) << 4);
-        found[c] = match ? f_c : found[c];
-        sts_u64_if(claim[c], a_cur + h[c] * 8u, mine[c]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const uint64_t back = lds_u64(a_cur + h[c] * 8u);
-        const bool p_c = (pend >> c) & 1u;
-        const bool won = claim[c] && back == mine[c];      // two positions may have claimed the same empty slot
-        h[c] = (p_c && !claim[c]) ? ((h[c] + 1u) & (kTabSlots - 1)) : h[c];
-        pend &= won ? ~(1u << c) : ~0u;
-      }
-    }
-    // ---- previous generation (read only), for the features not met in the current one
-    uint32_t look = 0;
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      look |= (((valid_bits >> c) & 1u) && found[c] == 0 && gen != 0) ? (1u << c) : 0u;
-      h[c] = scout_hash(k1[c] - 1u);
-    }
-    while (__any_sync(kFull, look != 0)) {
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const uint64_t cur = lds_u64(a_prev + h[c] * 8u);
-        const bool l_c = (look >> c) & 1u;
-        const bool match = l_c && static_cast<uint32_t>(cur >> 32) == k1[c];
-        const bool stop = match || cur == 0ull;
-        const uint32_t d = r + kGenRows - (static_cast<uint32_t>(cur >> 7) & 7u);
-        found[c] = (match && d <= wmax) ? (d | ((static_cast<uint32_t>(cur) & 127u) << 4)) : found[c];
-        h[c] = (h[c] + 1u) & (kTabSlots - 1);
-        look &= stop ? ~(1u << c) : ~0u;
-      }
-    }
     uint64_t code = 0ull;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
-      uint32_t f_c = ((found[c] & 15u) > wmax) ? 0u : found[c];   // an earlier row of this generation outside a short window
+      const uint32_t t1 = static_cast<uint32_t>(cur[c] >> 32);           // 0: no row of this epoch holds the feature yet
+      const uint32_t d = t + 1u - t1;                                    // >= 1 when t1 != 0
+      uint32_t f_c = (valid[c] && t1 != 0u && d <= wmax) ? (d | ((static_cast<uint32_t>(cur[c]) & 127u) << 4)) : 0u;
       // a row that ran serially touches every feature as far as the rows behind it are concerned
-      const bool use_long = ((valid_bits >> c) & 1u) && has_long && (f_c == 0 || dl < (f_c & 15u));
+      const bool use_long = valid[c] && has_long && (f_c == 0u || dl < (f_c & 15u));
       f_c = use_long ? (dl | kCodeGlobal) : f_c;
       code |= static_cast<uint64_t>(f_c) << (16 * c);
     }
@@ -940,6 +883,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
     return;
   }
   const bool free_run = (ra.flags & 1) != 0;
+  const uint64_t t_start = globaltimer_ns();
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int role = wave_role(warp, S);
@@ -988,7 +932,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
     if (role == S) {
       wave_producer(sm, f, ra, ep, q_base, n, lane);
     } else if (role == S + 1) {
-      wave_scout(sm, q_base, n, S - 1, lane);
+      wave_scout(sm, f.last_row, q_base, n, S - 1, lane);
     } else if (role == -2) {
       // idle placeholder of the chain warp's scheduler
     } else if (role == -1) {
@@ -1027,6 +971,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
       }
       w = w * wscale;
       st_state(k.st + j, w, gs, 0u);
+      f.last_row[j] = 0ull;
       f.W[j] = w;
       mc = fmax(mc, fabs(w - f.Wprev[j]));
       ms = fmax(ms, fabs(w));
@@ -1051,6 +996,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    pg.solver_ns += globaltimer_ns() - t_start;
     publish_progress(f.mirror, pg, ra.round_id);
   }
 }
@@ -1074,6 +1020,7 @@ saga_sparse_generic_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog
     return;
   }
   const bool free_run = (ra.flags & 1) != 0;
+  const uint64_t t_start = globaltimer_ns();
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int K = f.K, Ky = f.Ky, p = f.p;
@@ -1247,6 +1194,7 @@ saga_sparse_generic_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog
       f.codes[li] = (it_outer == f.max_iter) ? 1u : 0u;
       pg.npasses += it_outer;
     }
+    pg.solver_ns += globaltimer_ns() - t_start;
     publish_progress(f.mirror, pg, ra.round_id);
   }
 }
