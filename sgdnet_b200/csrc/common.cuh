@@ -61,8 +61,6 @@ struct FitDev {
   double *W, *gsum, *Wprev, *b, *gsi, *gmem;   // gmem [n][K]
   uint32_t* lag;             // [p]
   FeatState* st;             // [p] sparse K == 1: packed {W, gsum, lag} (then W mirrors st.w at epoch ends only)
-  uint64_t* last_row;        // [p] sparse K == 1: scout's table, (t + 1) << 32 | position for the last row of the epoch
-                             //     that holds the feature, 0 = none yet (wiped by the epoch-end sweep)
   double*   lag_scaling;     // [n+1] (unused when ls_identity)
   // ---- path
   const double *gamma, *alpha, *beta;   // per lambda

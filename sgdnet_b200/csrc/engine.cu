@@ -317,7 +317,7 @@ struct Engine {
     const bool wave = d.sparse && K == 1 && !pl.standardize;
     size_t epl = std::max<int64_t>(1, std::min<int64_t>(16, 200000 / std::max<int64_t>(1, d.n)));
     if (const char* env = std::getenv("SGDNET_EPOCHS_PER_LAUNCH")) epl = std::max(1, std::atoi(env));
-    size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 40 : 0) + (d.sparse ? (n + 1) * 8 : 0);
+    size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 32 : 0) + (d.sparse ? (n + 1) * 8 : 0);
     b += L * p * K * 8 + L * K * 8 + L * 24 + (pl.debug ? L * size_t(pl.max_iter) * 8 : 0);
     b += 2 * (epl * n * 4 + (epl + 1) * sizeof(MtState));
     b += size_t(sms) * 4 * 8 + sizeof(FitDev) + sizeof(Progress) + sizeof(MtState);
@@ -354,7 +354,6 @@ struct Engine {
     f.lag = arena.alloc<uint32_t>(p);
     job.variant = !d.sparse ? Variant::Dense : ((K == 1 && !f.standardize) ? Variant::SparseK1 : Variant::SparseGeneric);
     f.st = (job.variant == Variant::SparseK1) ? arena.alloc<FeatState>(p) : nullptr;
-    f.last_row = (job.variant == Variant::SparseK1) ? arena.alloc<uint64_t>(p) : nullptr;
     f.lag_scaling = d.sparse ? arena.alloc<double>(size_t(d.n) + 1, false) : nullptr;
     f.gamma = arena.upload(pl.gamma);
     f.alpha = arena.upload(pl.alpha);

@@ -139,8 +139,12 @@ struct __align__(128) WaveSmem {
   WaveSlotMeta meta[kWSlots];
   uint64_t full[kWSlots];
   uint64_t empty[kWSlots];
-  uint64_t coded[kWSlots];      // completes when the scout has written the slot's conflict codes and meta.dup
-  uint32_t samp[8];             // scout: sample ids of the last 8 rows
+  uint64_t coded[kWSlots];      // completes when both scout warps have written the slot's conflict codes and meta.dup
+  // scout: the last kHist rows' feature ids (by position, unused positions hold ~0) and hashed membership filters
+  uint32_t hidx[16][kCap];
+  uint32_t hbits[16][256];      // 8192 bits per row, two hash functions: ~0.06 % false positives at 100 entries
+  uint32_t hlong[16];           // the row was too long for a ring slot (ran serially)
+  uint32_t samp[8];             // sample ids of the last 8 rows
   uint64_t rdy[kSeq];
   uint64_t gok[kSeq];
   uint64_t fdone[kSeq];
@@ -297,82 +301,122 @@ __device__ __noinline__ void wave_producer(WaveSmem& sm, const FitDev& f, const 
   }
 }
 
-// ------------------------------------------------------------------ scout warp: conflict codes of the rows in the ring
-// Rows are taken in sequence order as their index runs land in the ring. last_row[j] (one 64-bit word per feature, L2
-// resident like the coefficient records) names the last row of this epoch that holds feature j and the feature's
-// position in it; per row the scout gathers the words of the row's features, derives the conflict codes from them
-// (distance = t - that row, if within the window) and scatters the row's own (t, position). A row's gather has to see
-// the scatter of the row before it: same warp, __syncwarp in between, L2-only accesses (.cg). Everything is straight
-// line: four independent loads and four predicated stores per lane and row. The table is wiped by the epoch-end
-// sweep (conflicts never cross an epoch boundary: that sweep rewrites every coefficient record).
-__device__ __forceinline__ uint64_t ldcg_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void stcg_u64_if(bool pred, uint64_t* p, uint64_t v) {
-  asm volatile(
-      "{\n"
-      ".reg .pred pp;\n"
-      "setp.ne.b32 pp, %2, 0;\n"
-      "@pp st.global.cg.u64 [%0], %1;\n"
-      "}\n" ::"l"(p),
-      "l"(v), "r"(static_cast<int>(pred))
-      : "memory");
-}
+// ------------------------------------------------------------------ scout warps: conflict codes of the rows in the ring
+// Two warps (the two spare warps of the chain's sub-partition) take every row in sequence order as its index run lands
+// in the ring; warp w owns the positions of chunks 2w and 2w + 1 (e = 64 w + lane, 64 w + 32 + lane). Per row both
+//   1. copy their positions' feature ids into a 16-row history and set two hashed bits per feature in the row's
+//      8192-bit membership filter; a named barrier between the two warps then makes the row's history and filter
+//      complete (and tells each warp that the other has finished the row before);
+//   2. test their features against the filters of the up to `window` rows before it; a filter hit is a candidate
+//      that the whole warp checks exactly by scanning that row's history (nearest row first), which also yields the
+//      feature's position in that row;
+//   3. write their half of the row's code words and arrive on the slot's `coded` barrier.
+// Everything lives in shared memory; a filter slot is wiped eight rows after it was last needed.
+constexpr int kHist = 16;
+__device__ __forceinline__ uint32_t scout_hash1(uint32_t j) { return (j * 2654435761u) >> 19; }                  // 13 bits
+__device__ __forceinline__ uint32_t scout_hash2(uint32_t j) { return (j * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
+__device__ __forceinline__ void scout_pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
-__device__ __noinline__ void wave_scout(WaveSmem& sm, uint64_t* __restrict__ last_row, uint32_t q_base, uint32_t n,
-                                        int window, int lane) {
+__device__ __noinline__ void wave_scout(WaveSmem& sm, uint32_t q_base, uint32_t n, int window, int w, int lane) {
   constexpr uint32_t kFull = 0xffffffffu;
-  if (lane < 8) sm.samp[lane] = 0xffffffffu;
-  __syncwarp();
-  uint32_t long_t = 0xffffffffu;       // most recent row of this epoch that was too long for a ring slot (none yet)
+  // wipe: filters (each warp its half of every row's words), long flags, sample ring
+  for (int i = lane; i < kHist * 128; i += 32) sm.hbits[i >> 7][w * 128 + (i & 127)] = 0u;
+  if (w == 0 && lane < kHist) sm.hlong[lane] = 0u;
+  if (w == 0 && lane < 8) sm.samp[lane] = 0xffffffffu;
+  scout_pair_sync();
   for (uint32_t t = 0; t < n; ++t) {
     const uint32_t q = q_base + t;
     const int slot = static_cast<int>(q % kWSlots);
+    const uint32_t hs = t & (kHist - 1);
     mbar_wait(&sm.full[slot], (q / kWSlots) & 1u);
     const uint32_t s_row = sm.meta[slot].s;
     const int nnz = sm.meta[slot].nnz;
     const bool is_long = nnz > kCap;
-    // ---- gather the table words of the row's features, then leave this row's (t, position) in their place
-    uint64_t cur[kChunks];
-    bool valid[kChunks];
-    uint32_t k[kChunks];
+    // ---- 1. this row's history and filter (own positions)
+    uint32_t k[2], h1[2], h2[2];
+    bool valid[2];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      const int e = c * 32 + lane;
+    for (int c = 0; c < 2; ++c) {
+      const int e = (2 * w + c) * 32 + lane;
       valid[c] = !is_long && e < nnz;
-      k[c] = valid[c] ? static_cast<uint32_t>(sm.idx[slot][e]) : 0u;     // clamped: invalid positions read word 0
+      k[c] = valid[c] ? static_cast<uint32_t>(sm.idx[slot][e]) : 0xffffffffu;
+      sm.hidx[hs][e] = k[c];
+      h1[c] = scout_hash1(k[c]);
+      h2[c] = scout_hash2(k[c]);
+      if (valid[c]) {
+        atomicOr(&sm.hbits[hs][h1[c] >> 5], 1u << (h1[c] & 31u));
+        atomicOr(&sm.hbits[hs][h2[c] >> 5], 1u << (h2[c] & 31u));
+      }
     }
-    __syncwarp();                      // the previous row's scatter (every lane's) precedes this row's gather
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) cur[c] = ldcg_u64(last_row + k[c]);
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c)
-      stcg_u64_if(valid[c], last_row + k[c], (static_cast<uint64_t>(t + 1u) << 32) | static_cast<uint64_t>(c * 32 + lane));
+    if (w == 0 && lane == 0) sm.hlong[hs] = is_long ? 1u : 0u;
+    scout_pair_sync();
+    // the filter that held row t - 8 (no row from here on looks that far back); it is rebuilt for row t + 8
+    *reinterpret_cast<uint4*>(&sm.hbits[(t + 8u) & (kHist - 1)][w * 128 + lane * 4]) = make_uint4(0u, 0u, 0u, 0u);
+    // ---- 2. candidates: filter hits in the rows of the window, bit d of hit[c] = row t - d
     const uint32_t wmax = t < static_cast<uint32_t>(window) ? t : static_cast<uint32_t>(window);
-    // the same sample drawn again inside the window (its gradient memory is in flight)
-    const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == s_row;
-    const uint32_t same_mask = __ballot_sync(kFull, same);
-    const uint32_t dupd = same_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(same_mask)) - 1) : 0u;
-    const bool has_long = long_t != 0xffffffffu && t - long_t <= wmax;
-    const uint32_t dl = has_long ? t - long_t : 0u;
-    uint64_t code = 0ull;
+    uint32_t hit[2] = {0u, 0u};
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      const uint32_t t1 = static_cast<uint32_t>(cur[c] >> 32);           // 0: no row of this epoch holds the feature yet
-      const uint32_t d = t + 1u - t1;                                    // >= 1 when t1 != 0
-      uint32_t f_c = (valid[c] && t1 != 0u && d <= wmax) ? (d | ((static_cast<uint32_t>(cur[c]) & 127u) << 4)) : 0u;
-      // a row that ran serially touches every feature as far as the rows behind it are concerned
-      const bool use_long = valid[c] && has_long && (f_c == 0u || dl < (f_c & 15u));
-      f_c = use_long ? (dl | kCodeGlobal) : f_c;
-      code |= static_cast<uint64_t>(f_c) << (16 * c);
+    for (uint32_t d = 1; d <= 7; ++d) {
+      const uint32_t ps = (t - d) & (kHist - 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t b1 = sm.hbits[ps][h1[c] >> 5] >> (h1[c] & 31u);
+        const uint32_t b2 = sm.hbits[ps][h2[c] >> 5] >> (h2[c] & 31u);
+        hit[c] |= (valid[c] && d <= wmax) ? ((b1 & b2 & 1u) << d) : 0u;
+      }
     }
-    long_t = is_long ? t : long_t;
-    sm.code[slot][lane] = code;
-    if (lane == 0) {
-      sm.meta[slot].dup = dupd;
-      sm.samp[t & 7u] = s_row;
+    // exact check of the candidates, nearest row first, by the whole warp
+    uint32_t found[2] = {0u, 0u};
+    for (;;) {
+      const uint32_t owners = __ballot_sync(kFull, (hit[0] | hit[1]) != 0u);
+      if (owners == 0u) break;
+      const int src = __ffs(static_cast<int>(owners)) - 1;
+      const int c_sel = hit[0] != 0u ? 0 : 1;
+      const uint32_t my_hits = hit[0] != 0u ? hit[0] : hit[1];
+      const uint32_t d_sel = static_cast<uint32_t>(__ffs(static_cast<int>(my_hits)) - 1);
+      const uint32_t bk = __shfl_sync(kFull, c_sel == 0 ? k[0] : k[1], src);
+      const uint32_t bd = __shfl_sync(kFull, d_sel, src);
+      const uint32_t ps = (t - bd) & (kHist - 1);
+      uint32_t pos = 0xffffffffu;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        const uint32_t mm = __ballot_sync(kFull, sm.hidx[ps][i * 32 + lane] == bk);
+        pos = (mm != 0u && pos == 0xffffffffu) ? static_cast<uint32_t>(i * 32 + __ffs(static_cast<int>(mm)) - 1) : pos;
+      }
+      if (lane == src) {
+        const bool ok = pos != 0xffffffffu;
+        const uint32_t f_new = d_sel | (pos << 4);
+        if (c_sel == 0) {
+          found[0] = ok ? f_new : found[0];
+          hit[0] = ok ? 0u : (hit[0] & ~(1u << d_sel));
+        } else {
+          found[1] = ok ? f_new : found[1];
+          hit[1] = ok ? 0u : (hit[1] & ~(1u << d_sel));
+        }
+      }
+    }
+    // a row that ran serially touches every feature as far as the rows behind it are concerned
+    const bool lng = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.hlong[(t - lane) & (kHist - 1)] != 0u;
+    const uint32_t long_mask = __ballot_sync(kFull, lng);
+    const uint32_t dl = long_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(long_mask)) - 1) : 0u;
+    uint32_t half = 0u;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t f_c = found[c];
+      const bool use_long = valid[c] && dl != 0u && (f_c == 0u || dl < (f_c & 15u));
+      f_c = use_long ? (dl | kCodeGlobal) : f_c;
+      half |= f_c << (16 * c);
+    }
+    // ---- 3. publish
+    reinterpret_cast<uint32_t*>(&sm.code[slot][lane])[w] = half;
+    if (w == 0) {
+      // the same sample drawn again inside the window (its gradient memory is in flight)
+      const bool same = lane >= 1 && static_cast<uint32_t>(lane) <= wmax && sm.samp[(t - lane) & 7u] == s_row;
+      const uint32_t same_mask = __ballot_sync(kFull, same);
+      if (lane == 0) {
+        sm.meta[slot].dup = same_mask ? static_cast<uint32_t>(__ffs(static_cast<int>(same_mask)) - 1) : 0u;
+        sm.samp[t & 7u] = s_row;
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.coded[slot]);
@@ -848,24 +892,15 @@ __device__ __noinline__ void wave_worker(WaveSmem& sm, const FitDev& f, const Wa
 // critical path of the whole fit, so it gets a scheduler to itself: it is warp 3 and the other warps of that
 // sub-partition (7, 11, ...) are idle placeholders that only take part in the block barriers and the epoch-end
 // sweep (measured: 648 -> 634 cycles per update on config 2's shape, 565 -> 539 without row conflicts).
-// Role index r = rank among the remaining warps: r < S workers, r == S the producer. The scout (role S + 1) is warp 7,
-// the second warp of the chain's sub-partition: a block of 12 warps leaves every thread the 168 registers the worker
-// needs (a 13th warp costs the workers spills); -DSGD_SCOUT_OWN_WARP puts it on a sub-partition of the workers instead.
-#ifdef SGD_SCOUT_OWN_WARP
-constexpr int wave_block_warps(int S) { return (S + 2) + (S + 2 - 1) / 3; }   // S+2 role warps on 3 of every 4 ids
+// Role index r = rank among the remaining warps: r < S workers, r == S the producer. The two scout warps (roles S + 1
+// and S + 2) are warps 7 and 11, the spare warps of the chain's sub-partition: a block of 12 warps leaves every thread
+// the 168 registers the worker needs.
+constexpr int wave_block_warps(int S) { return (S + 1) + (S + 1 + 2) / 3 < 12 ? 12 : (S + 1) + (S + 1 + 2) / 3; }
 __device__ __forceinline__ int wave_role(int warp, int S) {   // -1 chain, -2 idle, else role index
-  if ((warp & 3) == 3) return warp == 3 ? -1 : -2;
-  const int r = warp - (warp >> 2);
-  return r <= S + 1 ? r : -2;
-}
-#else
-constexpr int wave_block_warps(int S) { return (S + 1) + (S + 1 + 2) / 3 < 8 ? 8 : (S + 1) + (S + 1 + 2) / 3; }
-__device__ __forceinline__ int wave_role(int warp, int S) {   // -1 chain, -2 idle, else role index
-  if ((warp & 3) == 3) return warp == 3 ? -1 : (warp == 7 ? S + 1 : -2);
+  if ((warp & 3) == 3) return warp == 3 ? -1 : (warp == 7 ? S + 1 : (warp == 11 ? S + 2 : -2));
   const int r = warp - (warp >> 2);
   return r <= S ? r : -2;
 }
-#endif
 
 template <int S>
 __global__ void __launch_bounds__(wave_block_warps(S) * 32, 1)
@@ -910,7 +945,7 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
     for (int i = 0; i < kWSlots; ++i) {
       mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
-      mbar_init(&sm.coded[i], 1);
+      mbar_init(&sm.coded[i], 2);
     }
     for (int i = 0; i < kSeq; ++i) {
       mbar_init(&sm.rdy[i], 1);
@@ -931,8 +966,8 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep, q_base += n) {
     if (role == S) {
       wave_producer(sm, f, ra, ep, q_base, n, lane);
-    } else if (role == S + 1) {
-      wave_scout(sm, f.last_row, q_base, n, S - 1, lane);
+    } else if (role == S + 1 || role == S + 2) {
+      wave_scout(sm, q_base, n, S - 1, role - (S + 1), lane);
     } else if (role == -2) {
       // idle placeholder of the chain warp's scheduler
     } else if (role == -1) {
@@ -971,7 +1006,6 @@ saga_sparse_wave_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, c
       }
       w = w * wscale;
       st_state(k.st + j, w, gs, 0u);
-      f.last_row[j] = 0ull;
       f.W[j] = w;
       mc = fmax(mc, fabs(w - f.Wprev[j]));
       ms = fmax(ms, fabs(w));
@@ -1204,7 +1238,7 @@ int wave_warps() {
   static int s = [] {
     int v = 8;
     if (const char* env = std::getenv("SGDNET_WAVE_WARPS")) v = std::atoi(env);
-    return (v == 4 || v == 8) ? v : 8;     // the scout's tables cover a window of at most 7 rows
+    return v == 8 ? v : 8;     // the scouts' window is at most 7 rows and they are warps 7 and 11 of a 12-warp block
   }();
   return s;
 }
@@ -1222,7 +1256,6 @@ static cudaError_t launch_wave(FitDev* fit, Progress* prog, const RoundArgs& ra,
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   if (fast_k1) {
     switch (wave_warps()) {
-      case 4: return launch_wave<4>(fit, prog, ra, st);
       default: return launch_wave<8>(fit, prog, ra, st);
     }
   }
