@@ -28,9 +28,9 @@ ms = C.c_float(0)
 for it in range(3):
     lib.check(lib.sym("session_run_epochs")(sess, 30, 1, C.byref(rng), C.byref(ms)), "run")
 R = 4096
-buf = (C.c_longlong * (R * 10))()
+buf = (C.c_longlong * (R * 16))()
 lib.lib.sgdnet_debug_wave_trace(buf)
-a = np.array(buf[:], dtype=np.int64).reshape(R, 10)
+a = np.array(buf[:], dtype=np.int64).reshape(R, 16)
 np.save(os.path.join(ROOT, "gpurun_out", "wave_trace.npy"), a)
 print(f"epoch {ms.value:.1f} ms = {ms.value * 1e-3 * 1.965e9 / n:.0f} cycles/row (trace build), n={n} p={p}")
 a = a[8:-8]
@@ -55,3 +55,8 @@ print(f"worker row: full->done mean {np.mean(W7 - W3):.0f}; gok published->seen 
 S = 8
 nxt = W3[S:] - W7[:-S]
 print(f"worker: done(t) -> full(t+S) seen {nxt.mean():.0f}")
+
+S10, S11, S12, S13, W14 = [a[:, i].astype(np.float64) for i in (10, 11, 12, 13, 14)]
+print(f"scout: period {np.diff(S13).mean():.0f}; full seen->pair barrier {np.mean(S11 - S10):.0f}; barrier->tests done {np.mean(S12 - S11):.0f}; "
+      f"tests done->published {np.mean(S13 - S12):.0f}; published(t-1)->full seen(t) {np.mean(S10[1:] - S13[:-1]):.0f}")
+print(f"worker: full seen->coded seen {np.mean(W3 - W14):.0f}; scout published -> worker takes the row up {np.mean(W14 - S13):.0f} (negative: the worker waits for the scout)")

@@ -183,6 +183,8 @@ struct FitJob {
   bool have_handed_back = false;
   // ---- launch buffers, double buffered: [buf] is consumed by the launch in flight while [buf ^ 1] is prepared
   uint32_t* seq_dev[2] = {nullptr, nullptr};
+  uint64_t* dep_dev[2] = {nullptr, nullptr};   // sparse K == 1: conflict codes of the staged sequence (wave_deps_kernel)
+  uint8_t* dup_dev[2] = {nullptr, nullptr};
   MtState* snap_dev[2] = {nullptr, nullptr};   // [epochs_per_launch + 1] generator snapshots at epoch boundaries
   int epochs_per_launch = 1;
   int buf = 0;
@@ -319,7 +321,7 @@ struct Engine {
     if (const char* env = std::getenv("SGDNET_EPOCHS_PER_LAUNCH")) epl = std::max(1, std::atoi(env));
     size_t b = 3 * K * p * 8 + n * K * 8 + n * size_t(Ky) * 8 + p * 4 + (wave ? p * 32 : 0) + (d.sparse ? (n + 1) * 8 : 0);
     b += L * p * K * 8 + L * K * 8 + L * 24 + (pl.debug ? L * size_t(pl.max_iter) * 8 : 0);
-    b += 2 * (epl * n * 4 + (epl + 1) * sizeof(MtState));
+    b += 2 * (epl * n * 4 + (wave ? epl * n * 257 : 0) + (epl + 1) * sizeof(MtState));
     b += size_t(sms) * 4 * 8 + sizeof(FitDev) + sizeof(Progress) + sizeof(MtState);
     return b + 64 * Arena::kAlign;
   }
@@ -385,6 +387,10 @@ struct Engine {
     const int nbuf = job.device_rng ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) {
       job.seq_dev[b] = arena.alloc<uint32_t>(size_t(epl) * d.n, false);
+      if (job.variant == Variant::SparseK1) {
+        job.dep_dev[b] = arena.alloc<uint64_t>(size_t(epl) * d.n * 32, false);
+        job.dup_dev[b] = arena.alloc<uint8_t>(size_t(epl) * d.n, false);
+      }
       if (job.device_rng) job.snap_dev[b] = arena.alloc<MtState>(size_t(epl) + 1, false);
     }
     if (job.device_rng) {
@@ -511,6 +517,13 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------------------------- launches of one fit
+  // CTAs one fit's conflict-code pass may use: the GPU shared among the fits in flight
+  int deps_ctas() const {
+    int active = 0;
+    for (const FitJob& j : jobs) active += (j.phase != Phase::Done && j.phase != Phase::Parked) ? 1 : 0;
+    return std::max(8, sms * 6 / std::max(1, active));
+  }
+
   // the caller's generator -> device, at the start of run(); a launch prepared ahead stays valid when the caller hands
   // back the generator exactly as it received it
   void upload_rng(FitJob& j) {
@@ -535,7 +548,7 @@ struct Engine {
     const int ne = ne_fixed > 0 ? ne_fixed
                                 : static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(epl), std::max<uint32_t>(left, 1u)));
     const int b = j.buf;
-    RoundArgs ra{j.seq_dev[b], ne, flags, ++j.round_id, 0u};
+    RoundArgs ra{j.seq_dev[b], j.dep_dev[b], j.dup_dev[b], ne, flags, ++j.round_id, 0u};
     const int64_t n = j.dev.n;
     if (j.prepped) {
       CK(cudaStreamWaitEvent(j.st, j.ev_prep, 0));
@@ -557,6 +570,12 @@ struct Engine {
       }
       CK(cudaEventRecord(j.ev_idx, j.st));
       j.idx_on_prep = false;
+      if (j.variant == Variant::SparseK1) {
+        RoundArgs rd = ra;
+        rd.n_epochs = j.device_rng ? epl : ne;
+        CK(launch_wave_deps(j.dev_ptr, rd, n * rd.n_epochs, deps_ctas(), j.st));
+        ++j.launches;
+      }
     }
     if (j.variant != Variant::Dense) {
       CK(launch_lag_scaling(j.dev_ptr, j.prog_ptr, j.st));
@@ -577,13 +596,18 @@ struct Engine {
     j.t_submit = now_s();
     j.prepped = false;
     j.prepped_next = false;
-    // ---- the next launch's indices, generated on the second stream while this one runs, on the assumption that this
-    // launch consumes all `ne` epochs (it does unless the lambda converges inside it)
+    // ---- the next launch's indices and conflict codes, prepared on the second stream while this one runs, on the
+    // assumption that this launch consumes all `ne` epochs (it does unless the lambda converges inside it)
     if (j.device_rng && !no_overlap) {
       if (!j.idx_on_prep) CK(cudaStreamWaitEvent(j.st_prep, j.ev_idx, 0));
       const int nb = b ^ 1;
       CK(launch_mt_indices(j.snap_dev[b] + ne, static_cast<uint32_t>(n), epl, j.seq_dev[nb], j.snap_dev[nb], j.st_prep));
       ++j.launches;
+      if (j.variant == Variant::SparseK1) {
+        RoundArgs rd{j.seq_dev[nb], j.dep_dev[nb], j.dup_dev[nb], epl, 0, 0u, 0u};
+        CK(launch_wave_deps(j.dev_ptr, rd, n * epl, deps_ctas(), j.st_prep));
+        ++j.launches;
+      }
       CK(cudaEventRecord(j.ev_prep, j.st_prep));
       j.prepped_next = true;
     }

@@ -10,6 +10,8 @@ namespace sgd {
 // Per-fit arguments that change with every round of launches.
 struct RoundArgs {
   const uint32_t* seq;   // n * n_epochs sample indices for this launch
+  uint64_t* dep;         // sparse K == 1: [n * n_epochs][32] conflict codes written by wave_deps_kernel
+  uint8_t* dup;          // sparse K == 1: [n * n_epochs] distance to the last in-window row of the same sample
   int32_t n_epochs;      // epochs this launch may run (0 => the fit sits this round out)
   int32_t flags;         // bit 0: measurement mode - run exactly n_epochs, ignore convergence, stay kRunning
   uint32_t round_id;     // published with the fit's Progress when the launch is over (publish_progress)
@@ -26,6 +28,9 @@ cudaError_t launch_saga_dense(int K, int pen, size_t smem, FitDev* fit, Progress
 int dense_kt_bucket(int K);   // 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 
+// Conflict codes of a staged sequence for the wavefront kernel (sparse K == 1); a function of the sequence alone, so it
+// runs ahead of the solver launch that consumes it (on the fit's second stream, while the previous launch solves).
+cudaError_t launch_wave_deps(const FitDev* fit, const RoundArgs& ra, int64_t rows, int ctas, cudaStream_t st);
 int wave_warps();
 
 // R's Mersenne-Twister on the device (rng.cu): the sampling sequence of `n_epochs` epochs, floor(n * unif_rand()) per
