@@ -720,6 +720,8 @@ double* dup(const std::vector<double>& v) {
   return o;
 }
 
+thread_local bool g_path_only = false;   /* oracle_fit_batch_*: setup up to the lambda path only (sgdnet_fit_spec::path_only) */
+
 int fit_path(Design& d /* raw, samples-major */, std::vector<double> y /* n x Ky column-major */, int Ky,
              const sgdnet_control* ctl, sgdnet_rng* rng, sgdnet_result* out) {
   auto t_begin = std::chrono::steady_clock::now();
@@ -880,7 +882,7 @@ int fit_path(Design& d /* raw, samples-major */, std::vector<double> y /* n x Ky
 
   const bool group = (m.family == SGDNET_MGAUSSIAN) || (m.family == SGDNET_MULTINOMIAL && ctl->grouped_multinomial);
 
-  for (int li = 0; li < n_lambda; ++li) {
+  for (int li = 0; li < (g_path_only ? 0 : n_lambda); ++li) {
     SagaArgs a;
     a.pen = (mix == 0.0) ? RIDGE : (group ? GROUP : ENET);      /* sgdnet.cpp:80-99 */
     a.gamma = step_size[li];
@@ -922,6 +924,14 @@ int fit_path(Design& d /* raw, samples-major */, std::vector<double> y /* n x Ky
     losses_ptr.push_back(static_cast<int64_t>(all_losses.size()));
   }
 
+  if (g_path_only) {
+    a0_arch.assign(static_cast<size_t>(n_lambda) * K, 0.0);
+    beta_arch.assign(static_cast<size_t>(n_lambda) * p * K, 0.0);
+    dev_ratio.assign(n_lambda, 0.0);
+    codes.assign(n_lambda, 0u);
+    epochs.assign(n_lambda, 0u);
+    losses_ptr.assign(n_lambda + 1, 0);
+  }
   std::memset(out, 0, sizeof(*out));
   out->n_lambda = n_lambda;
   out->n_classes = K;
@@ -1103,6 +1113,86 @@ int oracle_score_deviance_sparse(const int32_t* csc_i, const int32_t* csc_p, con
   csc_to_design(csc_i, csc_p, csc_x, n, p, d);
   score_deviance(d, y, y_cols, family, a0, beta, n_lambda, n_classes, score);
   return SGDNET_OK;
+}
+
+/* The cv_sgdnet double loop (R/cv_sgdnet.R:160-200) one fit after the other: the sequential CPU counterpart of
+   sgdnet_fit_batch_* (same specs: row subsets, lambda_from, path_only, held-out deviance). */
+static void subset_design(const Design& d, const int32_t* rows, int64_t n_rows, Design& out) {
+  out.sparse = d.sparse;
+  out.p = d.p;
+  out.n = rows ? n_rows : d.n;
+  if (!rows) { out = d; return; }
+  if (d.sparse) {
+    out.rp.assign(1, 0);
+    out.ci.clear();
+    out.cv.clear();
+    for (int64_t i = 0; i < n_rows; ++i) {
+      const int64_t r = rows[i];
+      out.ci.insert(out.ci.end(), d.ci.begin() + d.rp[r], d.ci.begin() + d.rp[r + 1]);
+      out.cv.insert(out.cv.end(), d.cv.begin() + d.rp[r], d.cv.begin() + d.rp[r + 1]);
+      out.rp.push_back(static_cast<int64_t>(out.ci.size()));
+    }
+  } else {
+    out.dense.resize(static_cast<size_t>(n_rows) * d.p);
+    for (int64_t i = 0; i < n_rows; ++i)
+      std::memcpy(&out.dense[static_cast<size_t>(i) * d.p], &d.dense[static_cast<size_t>(rows[i]) * d.p], sizeof(double) * d.p);
+  }
+}
+
+static std::vector<double> subset_y(const double* y, int64_t n, int Ky, const int32_t* rows, int64_t n_rows) {
+  const int64_t m = rows ? n_rows : n;
+  std::vector<double> out(static_cast<size_t>(m) * Ky);
+  for (int k = 0; k < Ky; ++k)
+    for (int64_t i = 0; i < m; ++i) out[static_cast<size_t>(k) * m + i] = y[static_cast<size_t>(k) * n + (rows ? rows[i] : i)];
+  return out;
+}
+
+static int fit_batch_impl(const Design& raw, const double* y, int32_t y_cols, sgdnet_fit_spec* specs, int32_t n_fits,
+                          sgdnet_result* results, double* scores) {
+  int max_lambda = 0;
+  for (int i = 0; i < n_fits; ++i) max_lambda = std::max(max_lambda, specs[i].control.n_lambda);
+  for (int i = 0; i < n_fits; ++i) {
+    sgdnet_fit_spec& s = specs[i];
+    sgdnet_control ctl = s.control;
+    if (s.lambda_from >= 0) {
+      if (s.lambda_from >= i) { g_err = "lambda_from must name an earlier fit"; return SGDNET_ERR_ARG; }
+      ctl.lambda = results[s.lambda_from].lambda;
+      ctl.lambda_len = results[s.lambda_from].n_lambda;
+      ctl.n_lambda = ctl.lambda_len;
+    }
+    Design d;
+    subset_design(raw, s.train_rows, s.n_train, d);
+    g_path_only = s.path_only != 0;
+    const int rc = fit_path(d, subset_y(y, raw.n, y_cols, s.train_rows, s.n_train), y_cols, &ctl, &s.rng, &results[i]);
+    g_path_only = false;
+    if (rc != SGDNET_OK) return rc;
+    if (scores && !s.path_only && s.test_rows && s.n_test > 0) {
+      Design dt;
+      subset_design(raw, s.test_rows, s.n_test, dt);
+      const std::vector<double> yt = subset_y(y, raw.n, y_cols, s.test_rows, s.n_test);
+      std::vector<double> sc(results[i].n_lambda);
+      score_deviance(dt, yt.data(), y_cols, ctl.family, results[i].a0, results[i].beta, results[i].n_lambda, ctl.n_classes, sc.data());
+      std::memcpy(scores + static_cast<size_t>(i) * max_lambda, sc.data(), sizeof(double) * std::min<int>(results[i].n_lambda, max_lambda));
+    }
+  }
+  return SGDNET_OK;
+}
+
+int oracle_fit_batch_dense(const double* x, int64_t n, int64_t p, const double* y, int32_t y_cols, sgdnet_fit_spec* specs,
+                           int32_t n_fits, sgdnet_result* results, double* scores) {
+  if (!x || !y || !specs || !results || n_fits <= 0) { g_err = "null or empty argument"; return SGDNET_ERR_ARG; }
+  Design d;
+  colmajor_to_design(x, n, p, d);
+  return fit_batch_impl(d, y, y_cols, specs, n_fits, results, scores);
+}
+
+int oracle_fit_batch_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x, int64_t n, int64_t p,
+                            const double* y, int32_t y_cols, sgdnet_fit_spec* specs, int32_t n_fits,
+                            sgdnet_result* results, double* scores) {
+  if (!csc_i || !csc_p || !csc_x || !y || !specs || !results || n_fits <= 0) { g_err = "null or empty argument"; return SGDNET_ERR_ARG; }
+  Design d;
+  csc_to_design(csc_i, csc_p, csc_x, n, p, d);
+  return fit_batch_impl(d, y, y_cols, specs, n_fits, results, scores);
 }
 
 /* link[l][k][s] = a0[l][k] + x_s . beta[l][:,k]   (R/predict.sgdnet.R:377, 507-510) */

@@ -420,9 +420,15 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
     # needs its alpha's lambda path, which comes from the full fit's SETUP, not its solution (src/utils.h:157-165), so a
     # rank that does not own an alpha's full fit asks for that setup only (`path_only`).
     plan_costs = [float(len(w["train_rows"])) for w in plan]
-    owned = shard.mine([float(n)] * n_full + plan_costs)
-    my_full = [k for k in owned if k < n_full]
-    mine = [k - n_full for k in owned if k >= n_full]
+    use_batch = batched and lib.has("fit_batch_dense")
+    if use_batch:
+        all_costs = [float(n)] * n_full + plan_costs
+        owned = shard.mine(all_costs)
+        my_full = [k for k in owned if k < n_full]
+        mine = [k - n_full for k in owned if k >= n_full]
+    else:      # one call per fit: the full fits run on every rank (each needs their lambda paths), the fold fits are dealt
+        my_full = list(range(n_full))
+        mine = shard.mine(plan_costs)
     cv_rows = np.full((len(plan), opts["nlambda"] if lambdas[0] is None else max(len(l) for l in lambdas)), np.nan)
     fold_fits = [None] * len(plan)
     fits = [None] * n_full
@@ -434,7 +440,7 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
                              intercept=opts["intercept"], thresh=opts["thresh"],
                              standardize_response=opts["standardize_response"], debug=False)
 
-    if batched and lib.has("fit_batch_dense"):
+    if use_batch:
         # ONE batch per rank: its full-data fits (or just their lambda paths) and its fold fits, which take that path
         # through `lambda_from` - it is known after the full fit's setup, so all the fits run concurrently, each its
         # own pipeline on the device
@@ -462,7 +468,6 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
         # one call per fit (a backend without the batch entry point: the CPU oracle in the tests); unsharded full fits
         fits = [sgdnet(x, y, family=family, alpha=a, lambda_=lambdas[i], seed=fit_seeds[i], backend=lib, **opts)
                 for i, a in enumerate(alphas)]
-        my_full = list(range(n_full))
         lambdas = [f.lambda_ for f in fits]
         cv_rows = np.full((len(plan), max(len(l) for l in lambdas)), np.nan)
         yarr = np.asarray(y)
@@ -483,8 +488,8 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
         blocks.append(np.column_stack([np.full(len(lambdas[i]), a), lambdas[i], _summarize(cv_raw[i])]))
     optima = [_find_optimum(b) for b in blocks]
     best = int(np.argmin([o["error_min"] for o in optima]))
-    if shard.world > 1:            # the model the call returns lives on the rank that fitted it
-        owner = int(shard.owner_of([float(n)] * n_full + plan_costs)[best])
+    if shard.world > 1 and use_batch:     # the model the call returns lives on the rank that fitted it
+        owner = int(shard.owner_of(all_costs)[best])
         fits[best] = shard.broadcast_object(fits[best], src=owner)
     name = {"gaussian": "Mean-Squared Error", "mgaussian": "Mean-Squared Error", "binomial": "Binomial Deviance",
             "multinomial": "Multnomial Deviance"}[family]

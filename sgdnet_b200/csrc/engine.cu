@@ -246,6 +246,11 @@ struct Engine {
     t_begin = now_s();
   }
   ~Engine() {
+    PhaseTimer pt;
+    struct Lap {
+      PhaseTimer& t;
+      ~Lap() { t.lap("engine teardown"); }
+    } lap{pt};
     for (FitJob& j : jobs) {
       for (cudaEvent_t ev : {j.ev0, j.ev1, j.ev_idx, j.ev_prep, j.ev_f0, j.ev_f1})
         if (ev) cudaEventDestroy(ev);
@@ -1030,6 +1035,7 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
     if (scores) eng.upload_for_scoring();
     eng.finalize_batch();
     eng.run(-1, scores != nullptr);
+    pt.lap("run (all fits)");
     for (int i = 0; i < n_fits; ++i) {
       if (!eng.jobs[i].path_only) eng.settle_rng(eng.jobs[i]);
       eng.fill_result(i, &results[i]);
@@ -1038,6 +1044,7 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
         CK(cudaMemcpy(scores + size_t(i) * max_lambda, j.score_dev, sizeof(double) * std::min(j.plan.n_lambda, max_lambda),
                       cudaMemcpyDeviceToHost));
     }
+    pt.lap("results to the host");
     return SGDNET_OK;
   });
 }
