@@ -321,6 +321,7 @@ class CvSgdnet:
     name: str
     fits: list = field(default_factory=list)
     fold_fits: list = field(default_factory=list)
+    owned_full: list = field(default_factory=list)     # alphas whose full-data fit THIS rank ran (sharded runs)
 
 
 def _summarize(cv_raw):
@@ -495,4 +496,5 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
             "multinomial": "Multnomial Deviance"}[family]
     return CvSgdnet(alpha=alphas, lambda_=lambdas, cv_raw=cv_raw, cv_summary=np.vstack(blocks), fit=fits[best],
                     alpha_min=optima[best]["alpha_min"], lambda_min=optima[best]["lambda_min"],
-                    lambda_1se=optima[best]["lambda_1se"], name=name, fits=fits, fold_fits=fold_fits)
+                    lambda_1se=optima[best]["lambda_1se"], name=name, fits=fits, fold_fits=fold_fits,
+                    owned_full=list(my_full))
