@@ -66,6 +66,88 @@ __device__ __forceinline__ double sample_loss_warp(const FitDev& f, int K, int K
   return 0.5 * warp_sum(d);
 }
 
+// Sparse, K == 1, no virtual centring (configs 2 and 5): the bandwidth-bound form. A warp takes tiles of 32
+// consecutive rows: the 32 row descriptors and responses are one coalesced load each; the rows' index / value runs are
+// streamed four rows at a time (up to sixteen independent coalesced loads and as many 32-wide gathers of W in flight
+// per warp); a row's dot product keeps the association of the solver's (position e -> running sum e mod 32, then the
+// xor butterfly); the 32 linear predictors end up one per lane, so exp / log of the loss run ONCE per row instead of
+// 32 times, and the tile's 32 losses are added with one more butterfly. Partial sums: per warp in tile order, per
+// block in warp order, then the blocks in order (finish_lambda_kernel) - fixed, hence reproducible.
+__device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode, int lane, int64_t warp_global,
+                                                       int64_t warp_stride) {
+  const int64_t n = f.n;
+  const RowInfo* __restrict__ rows = f.rows;
+  const int32_t* __restrict__ ci = f.ci;
+  const double* __restrict__ cv = f.cv;
+  const double* __restrict__ W = f.W;
+  const double* __restrict__ yt = f.yt;
+  const double b0 = f.b[0];
+  const int family = f.family;
+  const double inv_n = 1.0;
+  (void)inv_n;
+  double acc = 0.0;
+  const int64_t n_tiles = (n + 31) / 32;
+  for (int64_t tile = warp_global; tile < n_tiles; tile += warp_stride) {
+    const int64_t s0 = tile * 32;
+    const int64_t s_mine = s0 + lane;
+    const bool have = s_mine < n;
+    RowInfo ri_mine{};
+    double y_mine = 0.0;
+    if (have) {
+      ri_mine = rows[s_mine];
+      y_mine = yt[s_mine];
+    }
+    double lp_mine = 0.0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+      if (s0 + r0 >= n) break;
+      int64_t st[4];
+      int nz[4];
+      double a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        st[u] = __shfl_sync(0xffffffffu, ri_mine.start, r0 + u);
+        nz[u] = __shfl_sync(0xffffffffu, ri_mine.nnz, r0 + u);      // 0 for rows past the end
+        a[u] = 0.0;
+      }
+      // the first four chunks of the four rows: sixteen independent load pairs
+      int32_t jj[4][4];
+      double vv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int e = c * 32 + lane;
+          const bool ok = e < nz[u];
+          jj[u][c] = ok ? ci[st[u] + e] : 0;
+          vv[u][c] = ok ? cv[st[u] + e] : 0.0;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double a2 = a[u] + vv[u][c] * W[jj[u][c]];
+          a[u] = (c * 32 + lane < nz[u]) ? a2 : a[u];
+        }
+      // rows longer than 128 nonzeros (rare): the rest of the row, same association
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        for (int e = 128 + lane; e < nz[u]; e += 32) a[u] += cv[st[u] + e] * W[ci[st[u] + e]];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) lp_mine = (lane == r0 + u) ? a[u] : lp_mine;
+    }
+    double loss = have ? loss_scalar(family, lp_mine + b0, y_mine) : 0.0;
+    if (mode == 1) loss = loss / static_cast<double>(static_cast<uint32_t>(n));
+    acc += warp_sum(loss);
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(kPassThreads)
 loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode) {
   __shared__ double wc_s[32];
@@ -80,56 +162,79 @@ loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, in
   const int64_t n = f.n;
   const double* __restrict__ W = f.W;
   const bool stdz = f.sparse && f.standardize;
-
-  // W . c per class (virtual centring), once per block
-  if (stdz) {
-    for (int k = 0; k < K; ++k) {
-      double a = 0.0;
-      for (int j = tid; j < p; j += blockDim.x) a += W[size_t(k) * p + j] * f.c[j];
-      a = warp_sum(a);
-      if (lane == 0) red2[warp * 32 + k] = a;
-    }
-    __syncthreads();
-    if (tid < K) {
-      double a = 0.0;
-      for (int w = 0; w < nwarps; ++w) a += red2[w * 32 + tid];
-      wc_s[tid] = a;
-    }
-    __syncthreads();
-  }
-
-  const double bk = (lane < K) ? f.b[lane] : 0.0;
-  double acc = 0.0;
   const int64_t warp_global = int64_t(blockIdx.x) * nwarps + warp;
   const int64_t warp_stride = int64_t(gridDim.x) * nwarps;
-  for (int64_t s = warp_global; s < n; s += warp_stride) {
-    double lp_lane = 0.0;
-    if (f.sparse) {
-      const RowInfo ri = f.rows[s];
-      const int32_t* __restrict__ ci = f.ci + ri.start;
-      const double* __restrict__ cv = f.cv + ri.start;
+  double acc = 0.0;
+
+  if (f.sparse && K == 1 && !stdz) {
+    acc = loss_tiles_sparse_k1(f, mode, lane, warp_global, warp_stride);
+  } else {
+    // W . c per class (virtual centring), once per block
+    if (stdz) {
       for (int k = 0; k < K; ++k) {
         double a = 0.0;
-        for (int e = lane; e < ri.nnz; e += 32) a += cv[e] * W[size_t(k) * p + ci[e]];
+        for (int j = tid; j < p; j += blockDim.x) a += W[size_t(k) * p + j] * f.c[j];
         a = warp_sum(a);
-        if (lane == k) lp_lane = a;
+        if (lane == 0) red2[warp * 32 + k] = a;
       }
-    } else {
-      const double* __restrict__ xr = f.xd + size_t(s) * ld;
-      for (int k = 0; k < K; ++k) {
+      __syncthreads();
+      if (tid < K) {
         double a = 0.0;
-        for (int j = lane; j < p; j += 32) a += W[size_t(k) * p + j] * xr[j];
-        a = warp_sum(a);
-        if (lane == k) lp_lane = a;
+        for (int w = 0; w < nwarps; ++w) a += red2[w * 32 + tid];
+        wc_s[tid] = a;
       }
+      __syncthreads();
     }
-    if (lane < K) {
-      lp_lane += bk;
-      if (stdz) lp_lane -= wc_s[lane];
+    const double bk = (lane < K) ? f.b[lane] : 0.0;
+    for (int64_t s = warp_global; s < n; s += warp_stride) {
+      double lp_lane = 0.0;
+      if (f.sparse) {
+        const RowInfo ri = f.rows[s];
+        const int32_t* __restrict__ ci = f.ci + ri.start;
+        const double* __restrict__ cv = f.cv + ri.start;
+        for (int k = 0; k < K; ++k) {
+          double a = 0.0;
+          for (int e = lane; e < ri.nnz; e += 32) a += cv[e] * W[size_t(k) * p + ci[e]];
+          a = warp_sum(a);
+          if (lane == k) lp_lane = a;
+        }
+      } else {
+        // the row is read once per group of four classes (config 4: once; config 3: three times, from L1 after the first)
+        const double* __restrict__ xr = f.xd + size_t(s) * ld;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          const double* __restrict__ W0 = W + size_t(k0) * p;
+          const double* __restrict__ W1 = W + size_t(k0 + 1 < K ? k0 + 1 : k0) * p;
+          const double* __restrict__ W2 = W + size_t(k0 + 2 < K ? k0 + 2 : k0) * p;
+          const double* __restrict__ W3 = W + size_t(k0 + 3 < K ? k0 + 3 : k0) * p;
+          for (int j = lane; j < p; j += 32) {
+            const double xj = xr[j];
+            a0 += W0[j] * xj;
+            a1 += W1[j] * xj;
+            a2 += W2[j] * xj;
+            a3 += W3[j] * xj;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+          }
+          if (lane == k0) lp_lane = a0;
+          if (lane == k0 + 1 && k0 + 1 < K) lp_lane = a1;
+          if (lane == k0 + 2 && k0 + 2 < K) lp_lane = a2;
+          if (lane == k0 + 3 && k0 + 3 < K) lp_lane = a3;
+        }
+      }
+      if (lane < K) {
+        lp_lane += bk;
+        if (stdz) lp_lane -= wc_s[lane];
+      }
+      double loss = sample_loss_warp(f, K, Ky, lp_lane, s, lane);
+      if (mode == 1) loss = loss / static_cast<double>(static_cast<uint32_t>(n));
+      acc += loss;
     }
-    double loss = sample_loss_warp(f, K, Ky, lp_lane, s, lane);
-    if (mode == 1) loss = loss / static_cast<double>(static_cast<uint32_t>(n));
-    acc += loss;
   }
   if (lane == 0) red_s[warp] = acc;
   __syncthreads();
