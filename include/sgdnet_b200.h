@@ -223,6 +223,20 @@ int sgdnet_predict_sparse(const int32_t* csc_i, const int32_t* csc_p, const doub
                           int64_t n, int64_t p,
                           const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes,
                           double* link);
+/* score() with any type.measure the family accepts (R/score.R:55-178): SGDNET_MEASURE_DEVIANCE / MSE / MAE for every
+   family, CLASS for binomial and multinomial, AUC for binomial. y as for the fits (binomial 0/1, multinomial class
+   ids). X * beta and the per-sample measures run on the device. AUC (R/score.R:203-232) is a rank statistic whose ties
+   R breaks with stats::runif, 2n draws per lambda: they are taken from `rng` (SGDNET_RNG_MT or SGDNET_RNG_CALLBACK;
+   ignored and may be NULL for the other measures) on the calling thread, and the sort runs on the host. */
+int sgdnet_score_dense(const double* x, int64_t n, int64_t p,
+                       const double* y, int32_t y_cols, int32_t family, int32_t measure,
+                       const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes,
+                       sgdnet_rng* rng, double* score);
+int sgdnet_score_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x,
+                        int64_t n, int64_t p,
+                        const double* y, int32_t y_cols, int32_t family, int32_t measure,
+                        const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes,
+                        sgdnet_rng* rng, double* score);
 int sgdnet_score_deviance_dense(const double* x, int64_t n, int64_t p,
                                 const double* y, int32_t y_cols, int32_t family,
                                 const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes,

@@ -1022,6 +1022,114 @@ void score_deviance(const Design& d, const double* y /* n x Ky col-major */, int
   }
 }
 
+/* score() for every type.measure (R/score.R:55-178; auc :203-232), on the linear predictors of predict.sgdnet
+   (R/predict.sgdnet.R:377, 437, 507-538). y: n x Ky column-major, binomial 0/1, multinomial class ids. */
+void score_measure(const Design& d, const double* y, int Ky, int family, int measure, const double* a0, const double* beta,
+                   int n_lambda, int K, sgdnet_rng* rng, double* score) {
+  if (measure == SGDNET_MEASURE_DEVIANCE) { score_deviance(d, y, Ky, family, a0, beta, n_lambda, K, score); return; }
+  const int64_t n = d.n, p = d.p;
+  std::vector<double> eta(static_cast<size_t>(n) * K);        /* [s][k] at one lambda */
+  std::vector<int> pred_all;                                   /* multinomial class: predicted class per (lambda, sample) */
+  if (family == SGDNET_MULTINOMIAL && measure == SGDNET_MEASURE_CLASS) pred_all.resize(static_cast<size_t>(n_lambda) * n);
+  for (int l = 0; l < n_lambda; ++l) {
+    const double* B = beta + static_cast<size_t>(l) * p * K;
+    const double* A = a0 + static_cast<size_t>(l) * K;
+    for (int64_t s = 0; s < n; ++s) {
+      double* lp = &eta[static_cast<size_t>(s) * K];
+      for (int k = 0; k < K; ++k) lp[k] = A[k];
+      if (d.sparse) {
+        for (int64_t e = d.rp[s]; e < d.rp[s + 1]; ++e)
+          for (int k = 0; k < K; ++k) lp[k] += d.cv[e] * B[static_cast<size_t>(d.ci[e]) * K + k];
+      } else {
+        for (int64_t j = 0; j < p; ++j)
+          for (int k = 0; k < K; ++k) lp[k] += d.dense[s * p + j] * B[static_cast<size_t>(j) * K + k];
+      }
+    }
+    double acc = 0.0;
+    if (family == SGDNET_GAUSSIAN) {
+      for (int64_t s = 0; s < n; ++s) {
+        const double r = eta[s] - y[s];
+        acc += (measure == SGDNET_MEASURE_MAE) ? std::fabs(r) : r * r;
+      }
+      score[l] = acc / static_cast<double>(n);
+    } else if (family == SGDNET_BINOMIAL) {
+      if (measure == SGDNET_MEASURE_AUC) {
+        /* auc(): doubled data, ties broken by runif (2n draws), weighted rank sum */
+        std::vector<double> r(static_cast<size_t>(2 * n));
+        for (double& v : r) v = mt_unif(rng);
+        std::vector<int64_t> order(static_cast<size_t>(2 * n));
+        for (int64_t i = 0; i < 2 * n; ++i) order[i] = i;
+        auto prob = [&](int64_t i) { return 1.0 / (1.0 + std::exp(-eta[i % n])); };
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+          const double pa = prob(a), pb = prob(b);
+          if (pa != pb) return pa < pb;
+          return r[a] < r[b];
+        });
+        double cw = 0.0, cw1 = 0.0, total = 0.0;
+        for (int64_t idx : order) {
+          const bool is_one = idx >= n;                                  /* rep(c(0, 1), c(ny, ny)) */
+          const double y2 = (y[idx % n] > 0.5) ? 1.0 : 0.0;
+          const double w = is_one ? y2 : 1.0 - y2;                        /* as.vector(weights * y) */
+          cw += w;
+          if (is_one) { cw1 += w; total += w * (cw - cw1); }
+        }
+        score[l] = std::exp(std::log(total) - std::log(cw1) - std::log(cw - cw1));
+        continue;
+      }
+      for (int64_t s = 0; s < n; ++s) {
+        const double pr = 1.0 / (1.0 + std::exp(-eta[s]));
+        const double y2 = (y[s] > 0.5) ? 1.0 : 0.0, y1 = 1.0 - y2;
+        if (measure == SGDNET_MEASURE_CLASS) acc += y1 * (pr > 0.5 ? 1.0 : 0.0) + y2 * (pr <= 0.5 ? 1.0 : 0.0);
+        else {
+          const double u = (pr + y1) - 1.0, v = pr - y2;
+          acc += (measure == SGDNET_MEASURE_MAE) ? std::fabs(u) + std::fabs(v) : u * u + v * v;
+        }
+      }
+      score[l] = acc / static_cast<double>(n);
+    } else if (family == SGDNET_MULTINOMIAL) {
+      for (int64_t s = 0; s < n; ++s) {
+        const double* lp = &eta[static_cast<size_t>(s) * K];
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) tot += std::exp(lp[k]);
+        const unsigned cls = static_cast<unsigned>(y[s] + 0.5);
+        double best = 0.0;
+        int best_k = 0;
+        for (int k = 0; k < K; ++k) {
+          const double pk = std::exp(lp[k]) / tot;
+          const double yk = (static_cast<unsigned>(k) == cls) ? 1.0 : 0.0;
+          if (measure == SGDNET_MEASURE_MSE) acc += (yk - pk) * (yk - pk);
+          else if (measure == SGDNET_MEASURE_MAE) acc += std::fabs(yk - pk);
+          if (k == 0 || pk > best) { best = pk; best_k = k; }
+        }
+        if (measure == SGDNET_MEASURE_CLASS) pred_all[static_cast<size_t>(l) * n + s] = best_k;
+      }
+      score[l] = acc / static_cast<double>(n);
+    } else {
+      for (int64_t s = 0; s < n; ++s)
+        for (int k = 0; k < K; ++k) {
+          const double r = eta[static_cast<size_t>(s) * K + k] - y[static_cast<size_t>(k) * n + s];
+          acc += (measure == SGDNET_MEASURE_MAE) ? std::fabs(r) : r * r;
+        }
+      score[l] = acc / K;
+    }
+  }
+  if (!pred_all.empty()) {
+    /* classid <- as.numeric(as.factor(.)) over ALL samples and lambdas: ranks among the classes predicted anywhere */
+    std::vector<int> present(K, 0), code(K, 0);
+    for (int c : pred_all) present[c] = 1;
+    int rank = 0;
+    for (int k = 0; k < K; ++k) { code[k] = rank; rank += present[k]; }
+    for (int l = 0; l < n_lambda; ++l) {
+      double acc = 0.0;
+      for (int64_t s = 0; s < n; ++s) {
+        const unsigned cls = static_cast<unsigned>(y[s] + 0.5);
+        acc += 1.0 - ((static_cast<unsigned>(code[pred_all[static_cast<size_t>(l) * n + s]]) == cls) ? 1.0 : 0.0);
+      }
+      score[l] = acc / static_cast<double>(n);
+    }
+  }
+}
+
 void csc_to_design(const int32_t* ci, const int32_t* cp, const double* cx, int64_t n, int64_t p, Design& d) {
   d.sparse = true;
   d.n = n;
@@ -1112,6 +1220,25 @@ int oracle_score_deviance_sparse(const int32_t* csc_i, const int32_t* csc_p, con
   Design d;
   csc_to_design(csc_i, csc_p, csc_x, n, p, d);
   score_deviance(d, y, y_cols, family, a0, beta, n_lambda, n_classes, score);
+  return SGDNET_OK;
+}
+
+int oracle_score_dense(const double* x, int64_t n, int64_t p, const double* y, int32_t y_cols, int32_t family, int32_t measure,
+                       const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes, sgdnet_rng* rng, double* score) {
+  if (measure == SGDNET_MEASURE_AUC && !rng) { g_err = "auc needs a generator"; return SGDNET_ERR_RNG; }
+  Design d;
+  colmajor_to_design(x, n, p, d);
+  score_measure(d, y, y_cols, family, measure, a0, beta, n_lambda, n_classes, rng, score);
+  return SGDNET_OK;
+}
+
+int oracle_score_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x, int64_t n, int64_t p, const double* y,
+                        int32_t y_cols, int32_t family, int32_t measure, const double* a0, const double* beta, int32_t n_lambda,
+                        int32_t n_classes, sgdnet_rng* rng, double* score) {
+  if (measure == SGDNET_MEASURE_AUC && !rng) { g_err = "auc needs a generator"; return SGDNET_ERR_RNG; }
+  Design d;
+  csc_to_design(csc_i, csc_p, csc_x, n, p, d);
+  score_measure(d, y, y_cols, family, measure, a0, beta, n_lambda, n_classes, rng, score);
   return SGDNET_OK;
 }
 

@@ -226,6 +226,9 @@ class Library:
             if self.has("score_deviance_" + nm):
                 f = self.sym("score_deviance_" + nm)
                 f.argtypes = xa + [c_double_p, C.c_int32, C.c_int32] + coef + [c_double_p]; f.restype = C.c_int
+            if self.has("score_" + nm):
+                f = self.sym("score_" + nm)
+                f.argtypes = xa + [c_double_p, C.c_int32, C.c_int32, C.c_int32] + coef + [C.POINTER(Rng), c_double_p]; f.restype = C.c_int
             if self.has("fit_batch_" + nm):
                 f = self.sym("fit_batch_" + nm)
                 f.argtypes = xa + [c_double_p, C.c_int32, C.POINTER(FitSpec), C.c_int32, C.POINTER(Result), c_double_p]
@@ -371,6 +374,20 @@ class Library:
         self.check(rc, "predict_" + kind)
         return out
 
+    def score(self, x, y, family: int, measure: str, a0: np.ndarray, beta: np.ndarray, rng: Optional[Rng] = None) -> np.ndarray:
+        """score() for one type.measure (R/score.R); `rng` supplies auc's tie-breaking draws and is advanced in place."""
+        kind, xargs, _keep = self._x_args(x)
+        L, p, K = beta.shape
+        ya = _as_f64(np.asarray(y, dtype=np.float64).reshape(len(y), -1))
+        a0c = np.ascontiguousarray(a0, dtype=np.float64).reshape(L, K)
+        bc = np.ascontiguousarray(beta, dtype=np.float64)
+        out = np.empty(L)
+        rc = self.sym("score_" + kind)(*xargs, _ptr(ya, c_double_p), C.c_int32(ya.shape[1]), C.c_int32(family),
+                                       C.c_int32(MEASURES[measure]), _ptr(a0c, c_double_p), _ptr(bc, c_double_p), C.c_int32(L),
+                                       C.c_int32(K), C.byref(rng) if rng is not None else None, _ptr(out, c_double_p))
+        self.check(rc, "score_" + kind)
+        return out
+
     def score_deviance(self, x, y, family: int, a0: np.ndarray, beta: np.ndarray) -> np.ndarray:
         kind, xargs, _keep = self._x_args(x)
         L, p, K = beta.shape
@@ -384,6 +401,8 @@ class Library:
         self.check(rc, "score_deviance_" + kind)
         return out
 
+
+MEASURES = {"deviance": 0, "mse": 1, "mae": 2, "class": 3, "auc": 4}
 
 _PRODUCT: Optional[Library] = None
 

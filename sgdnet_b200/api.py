@@ -282,29 +282,35 @@ def deviance(fit: SgdnetFit):
     return (1.0 - fit.dev_ratio) * fit.nulldev
 
 
-def score(fit: SgdnetFit, x, y, type_measure: str = "deviance", backend: Optional[Library] = None):
-    """score.sgdnet_* with type.measure = "deviance" on the device (R/score.R:55-178); mse/mae/class
-    are computed from predict() output as in R."""
+MEASURES_OF = {"gaussian": ("deviance", "mse", "mae"), "binomial": ("deviance", "mse", "mae", "class", "auc"),
+               "multinomial": ("deviance", "mse", "mae", "class"), "mgaussian": ("deviance", "mse", "mae")}
+
+
+def _encode_for_score(family: str, y):
+    if family in ("binomial", "multinomial"):
+        levels = np.unique(np.asarray(y).reshape(-1))
+        return np.searchsorted(levels, np.asarray(y).reshape(-1)).astype(np.float64).reshape(-1, 1)
+    return np.asarray(y, dtype=np.float64).reshape(len(y), -1)
+
+
+def score(fit: SgdnetFit, x, y, type_measure: str = "deviance", backend: Optional[Library] = None,
+          rng: Optional[_abi.Rng] = None):
+    """score.sgdnet_* (R/score.R:55-178), every type.measure of the family, on the device: X * beta and the per-sample
+    terms in one pass over the rows. `rng` (R's generator) supplies auc's tie-breaking draws (R/score.R:218)."""
     lib = backend or _abi.product()
+    if type_measure not in MEASURES_OF[fit.family]:
+        raise ValueError(f"'arg' should be one of {MEASURES_OF[fit.family]}")
     mats_l = _stack_coef(fit)
     a0 = np.stack([m[0, :] for m in mats_l], axis=1)
     beta = np.stack([m[1:, :].T for m in mats_l], axis=2)
-    fam = FAMILIES[fit.family]
-    if type_measure == "deviance" or (type_measure == "mse" and fit.family in ("gaussian", "mgaussian")):
-        if fit.family in ("binomial", "multinomial"):
-            levels = np.unique(np.asarray(y).reshape(-1))
-            yv = np.searchsorted(levels, np.asarray(y).reshape(-1)).astype(np.float64).reshape(-1, 1)
-        else:
-            yv = np.asarray(y, dtype=np.float64).reshape(len(y), -1)
-        return lib.score_deviance(x, yv, fam, a0, beta)
-    if type_measure == "mae" and fit.family == "gaussian":
-        return np.abs(predict(fit, x, backend=lib) - np.asarray(y, float).reshape(-1, 1)).mean(axis=0)
-    if type_measure == "class" and fit.family == "binomial":
-        pr = predict(fit, x, type="response", backend=lib)
-        levels = np.unique(np.asarray(y).reshape(-1))
-        y1 = (np.asarray(y).reshape(-1) == levels[1]).astype(float)[:, None]
-        return ((1 - y1) * (pr > 0.5) + y1 * (pr <= 0.5)).mean(axis=0)
-    raise NotImplementedError(f"type.measure '{type_measure}' for family '{fit.family}' stays in R (SURVEY.md section 2, row 13)")
+    yv = _encode_for_score(fit.family, y)
+    if lib.has("score_dense"):
+        if type_measure == "auc" and rng is None:
+            rng = lib.rng_from_seed(1)
+        return lib.score(x, yv, FAMILIES[fit.family], type_measure, a0, beta, rng=rng)
+    if type_measure != "deviance":
+        raise NotImplementedError(f"this backend only scores type.measure = 'deviance'")
+    return lib.score_deviance(x, yv, FAMILIES[fit.family], a0, beta)
 
 
 # ------------------------------------------------------------------------------------------- cv
@@ -375,8 +381,10 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
     `fits[i]` is None on ranks that do not own alpha i's full fit.
     """
     lib = backend or _abi.product()
-    if type_measure != "deviance":
-        raise NotImplementedError("only type.measure = 'deviance' runs on the device")
+    if type_measure not in MEASURES_OF[family]:
+        raise ValueError(f"'arg' should be one of {MEASURES_OF[family]}")
+    if type_measure == "auc":
+        batched = False          # auc is scored one fit at a time: its tie-breaking draws come from the caller's generator
     alphas = list(np.atleast_1d(alpha))
     if not (nfolds > 2 and len(alphas) > 0):
         raise ValueError("nfolds > 2, is.numeric(alpha), length(alpha) > 0 are not all TRUE")
@@ -456,7 +464,7 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
             ctl, keep = control_for(w["alpha"], lambdas[w["alpha_index"]], len(w["train_rows"]))
             keeps.append(keep)
             specs.append(dict(train_rows=w["train_rows"], test_rows=w["test_rows"], control=ctl,
-                              rng=lib.rng_from_seed(fit_seeds[n_full + k]),
+                              rng=lib.rng_from_seed(fit_seeds[n_full + k]), measure=_abi.MEASURES[type_measure],
                               lambda_from=w["alpha_index"] if lambdas[w["alpha_index"]] is None else -1))
         raws, scores = lib.fit_batch(x, ymat, specs)
         lambdas = [raw.lambda_.copy() for raw in raws[:n_full]]
@@ -477,7 +485,7 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
             f = sgdnet(_rows(x, w["train_rows"]), yarr[w["train_rows"]], family=family, alpha=w["alpha"],
                        lambda_=lambdas[w["alpha_index"]], seed=fit_seeds[n_full + k], backend=lib, **opts)
             fold_fits[k] = f
-            cv_rows[k, :len(f.lambda_)] = score(f, _rows(x, w["test_rows"]), yarr[w["test_rows"]], "deviance", backend=lib)
+            cv_rows[k, :len(f.lambda_)] = score(f, _rows(x, w["test_rows"]), yarr[w["test_rows"]], type_measure, backend=lib)
     cv_rows = shard.all_gather_rows(cv_rows, mine)
 
     cv_raw = []
@@ -492,8 +500,9 @@ def cv_sgdnet(x, y, alpha=1.0, lambda_=None, nfolds: int = 10, foldid=None, type
     if shard.world > 1 and use_batch:     # the model the call returns lives on the rank that fitted it
         owner = int(shard.owner_of(all_costs)[best])
         fits[best] = shard.broadcast_object(fits[best], src=owner)
-    name = {"gaussian": "Mean-Squared Error", "mgaussian": "Mean-Squared Error", "binomial": "Binomial Deviance",
-            "multinomial": "Multnomial Deviance"}[family]
+    name = {"deviance": {"gaussian": "Mean-Squared Error", "mgaussian": "Mean-Squared Error", "binomial": "Binomial Deviance",
+                         "multinomial": "Multnomial Deviance"}[family],
+            "mse": "Mean-Squared Error", "mae": "Mean Absolute Error", "class": "Misclassification Error", "auc": "AUC"}[type_measure]
     return CvSgdnet(alpha=alphas, lambda_=lambdas, cv_raw=cv_raw, cv_summary=np.vstack(blocks), fit=fits[best],
                     alpha_min=optima[best]["alpha_min"], lambda_min=optima[best]["lambda_min"],
                     lambda_1se=optima[best]["lambda_1se"], name=name, fits=fits, fold_fits=fold_fits,

@@ -24,6 +24,7 @@ enum Penalty : int { kRidge = 0, kElasticNet = 1, kGroupLasso = 2 };
 enum Status : int { kRunning = 0, kLambdaDone = 1, kFitDone = 2 };
 
 constexpr int kMaxClasses = 64;   // K handled by one warp in the gradient step
+constexpr int kRescaleBlocks = 64; // CTAs of the per-lambda rescale + archive pass
 
 // One padded CSR row: `start` is a multiple of 4 entries so that the index run (int32) and the value run (double)
 // both begin on 16-byte boundaries, which is what cp.async.bulk needs. Pad entries are never read as data.
@@ -77,6 +78,8 @@ struct FitDev {
   double *losses;            // debug: [n_lambda * max_iter] or null
   // ---- scratch
   double *partials;          // per-block partial sums for the grid-wide passes
+  double *xb_partials;       // [kRescaleBlocks][K] per-block sums of x_center_j * beta_j (Rescale)
+  uint32_t *nz_mask;         // [ceil(p/32)] sparse K == 1: bit j set iff W[j] != 0 at the last rescale (deviance pass)
   int32_t debug;
   int32_t pad0_;             // always 0 (read as a run-time zero, see dep_on)
   struct Progress* mirror;   // pinned host copy of the fit's Progress, written by the kernels that change it

@@ -200,6 +200,7 @@ struct FitJob {
   bool needs_finish = false;          // the last solver launch ended a lambda (or, debug mode, an epoch): passes are due
   bool stale_prep = false;            // a prepared launch was discarded; its kernels may still be running on st_prep
   int loss_blocks = 1;
+  int mask_words = 0;                 // sparse K == 1: words of the nonzero-coefficient bitmap (0: p too large for it)
   size_t dense_smem = 0;
   double seconds_solver = 0.0, seconds_dev = 0.0;
   uint64_t launches = 0;
@@ -407,6 +408,10 @@ struct Engine {
     // streaming passes: enough CTAs to fill the GPU when the fit's pass runs alone
     job.loss_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(int64_t(sms) * 4, (d.n + 7) / 8)));
     f.partials = arena.alloc<double>(job.loss_blocks);
+    f.xb_partials = arena.alloc<double>(size_t(kRescaleBlocks) * K);
+    const int mask_words = (p + 31) / 32;
+    job.mask_words = (job.variant == Variant::SparseK1 && mask_words * 4 <= 40 * 1024) ? mask_words : 0;
+    f.nz_mask = job.mask_words ? arena.alloc<uint32_t>(mask_words) : nullptr;
     if (job.variant == Variant::Dense) {
       int in_smem = 0;
       job.dense_smem = dense_smem_bytes(K, p, d.ld, &in_smem);
@@ -658,8 +663,8 @@ struct Engine {
       CK(launch_epoch_loss(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.st));
       j.launches += 2;
     }
-    CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.round_id, j.st));
-    j.launches += 2;
+    CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.mask_words, j.round_id, j.st));
+    j.launches += 3;
     if (use_events()) CK(cudaEventRecord(j.ev_f1, j.st));
     j.phase = Phase::Finish;
   }
@@ -824,9 +829,12 @@ struct Engine {
     raw_uploaded = true;
   }
 
-  // score/link of rows `row_ids` (device pointer or null) under coefficients (a0_dev, beta_dev), on stream `st`
+  // score/link of rows `row_ids` (device pointer or null) under coefficients (a0_dev, beta_dev), on stream `st`.
+  // `measure`: SGDNET_MEASURE_* (R/score.R:55-178). Multinomial "class" may need a second pass (see the kernel): the
+  // call then waits for the first one on `st`.
   uint64_t predict_score(int family, int K, int L, const int32_t* row_ids_dev, int64_t n_rows, const double* a0_dev,
-                         const double* beta_dev, bool with_y, double* link_dev, double* score_dev, cudaStream_t st) {
+                         const double* beta_dev, bool with_y, double* link_dev, double* score_dev, cudaStream_t st,
+                         int measure = SGDNET_MEASURE_DEVIANCE) {
     upload_raw();
     const HostDesign& hd = *designs[std::make_pair((const int32_t*)nullptr, 0)].first;
     PredictArgs a{};
@@ -837,6 +845,7 @@ struct Engine {
     a.p = hd.p;
     a.ld = hd.ld;
     a.n_lambda = L;
+    a.measure = measure;
     a.n = n_rows;
     a.row_ids = row_ids_dev;
     a.xd = raw_dev.xd;
@@ -851,11 +860,40 @@ struct Engine {
     a.partials = arena.alloc<double>(size_t(blocks) * L, false);     // every entry is written by its block
     a.score = score_dev;
     double* bt = arena.alloc<double>(size_t(hd.p) * L * K, false);
-    CK(launch_predict_score(a, bt, blocks, st));
-    return score_dev ? 3 : 2;
+    uint64_t launches = score_dev ? 3 : 2;
+    const bool two_pass = with_y && family == kMultinomial && measure == SGDNET_MEASURE_CLASS;
+    uint32_t* present_dev = nullptr;
+    if (two_pass) {
+      present_dev = arena.alloc<uint32_t>(1, false);
+      CK(cudaMemsetAsync(present_dev, 0, sizeof(uint32_t), st));
+      a.present = present_dev;
+    }
+    CK(launch_predict_score(a, bt, blocks, st, true));
+    if (two_pass) {
+      uint32_t present = 0;
+      CK(cudaMemcpyAsync(&present, present_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const uint32_t all = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+      if ((present & all) != all) {
+        // some class is never predicted: as.numeric(as.factor(.)) numbers the predicted classes 1, 2, ... in order
+        std::vector<int32_t> remap(K, 0);
+        int32_t rank = 0;
+        for (int k = 0; k < K; ++k) {
+          remap[k] = rank;
+          if (present & (1u << k)) ++rank;
+        }
+        int32_t* remap_dev = arena.alloc<int32_t>(K, false);
+        CK(cudaMemcpyAsync(remap_dev, remap.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+        a.remap = remap_dev;
+        a.present = nullptr;
+        CK(launch_predict_score(a, bt, blocks, st, false));
+        CK(cudaStreamSynchronize(st));       // `remap` lives on this stack frame
+        launches += 2;
+      }
+    }
+    return launches;
   }
 
-  // score(fit, x_test, y_test) of a finished fit, on the fit's own stream (R/cv_sgdnet.R:197-198)
   // held-out rows and the raw design / response on the device, before the batch starts (see finalize_batch)
   void upload_for_scoring() {
     bool any = false;
@@ -876,7 +914,7 @@ struct Engine {
     const int L = j.plan.n_lambda;
     j.score_dev = arena.alloc<double>(L, false);
     j.launches += predict_score(j.plan.family, j.plan.K, L, td, j.n_test, j.dev.a0_arch, j.dev.beta_arch, true, nullptr,
-                                j.score_dev, j.st);
+                                j.score_dev, j.st, j.measure);
     j.scored = true;
   }
 };
@@ -949,6 +987,51 @@ int fit_single(const XArg& xa, const double* y, int32_t y_cols, const sgdnet_con
   });
 }
 
+bool measure_ok(int family, int measure, std::string& why) {
+  // the measures each family's score() accepts (R/score.R:58, 78-82, 124-127, 165)
+  const bool binomial = family == SGDNET_BINOMIAL, multinomial = family == SGDNET_MULTINOMIAL;
+  if (measure < SGDNET_MEASURE_DEVIANCE || measure > SGDNET_MEASURE_AUC) { why = "unknown type.measure"; return false; }
+  if (measure == SGDNET_MEASURE_CLASS && !(binomial || multinomial)) { why = "type.measure 'class' needs a binomial or multinomial fit"; return false; }
+  if (measure == SGDNET_MEASURE_AUC && !binomial) { why = "type.measure 'auc' needs a binomial fit"; return false; }
+  return true;
+}
+
+// auc(y, prob) of R/score.R:203-232 for one lambda, from the probabilities the device computed. The reference doubles
+// the data (every observation once as a 0 with weight y1, once as a 1 with weight y2), breaks ties in `prob` with
+// stats::runif - one draw per doubled observation, 2n per lambda, taken here from the caller's generator on the calling
+// thread - and sums, over the observations of the second class, the weight of the first-class observations ordered
+// before them. Only the entries with weight 1 matter: first-class observation i carries draw r[i], second-class
+// observation i draw r[n + i]; on a full tie the first-class entry comes first (it has the smaller index).
+double auc_one_lambda(const double* eta, const double* y, int64_t n, sgdnet_rng* rng) {
+  std::vector<double> r(static_cast<size_t>(2 * n));
+  for (double& v : r) v = (rng->kind == SGDNET_RNG_CALLBACK) ? rng->unif_rand(rng->ctx) : mt_unif(rng);
+  struct Item {
+    double prob, r;
+    int32_t pos;      // 0: first class (y == 0), 1: second class
+  };
+  std::vector<Item> items(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i) {
+    const bool second = y[i] > 0.5;
+    items[i] = Item{1.0 / (1.0 + std::exp(-eta[i])), second ? r[n + i] : r[i], second ? 1 : 0};
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+    if (a.prob != b.prob) return a.prob < b.prob;
+    if (a.r != b.r) return a.r < b.r;
+    return a.pos < b.pos;
+  });
+  double first_seen = 0.0, u = 0.0, n1 = 0.0;
+  for (const Item& it : items) {
+    if (it.pos) {
+      u += first_seen;
+      n1 += 1.0;
+    } else {
+      first_seen += 1.0;
+    }
+  }
+  const double n0 = static_cast<double>(n) - n1;
+  return std::exp(std::log(u) - std::log(n1) - std::log(n0));
+}
+
 int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* specs, int32_t n_fits,
               sgdnet_result* results, double* scores) {
   std::string why;
@@ -963,6 +1046,11 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
     for (int i = 0; i < n_fits; ++i) {
       const sgdnet_fit_spec& s = specs[i];
       if (s.lambda_from >= i) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": lambda_from must name an earlier fit");
+      std::string mwhy;
+      if (scores && s.test_rows && !measure_ok(s.control.family, s.measure, mwhy)) return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": " + mwhy);
+      if (scores && s.test_rows && s.measure == SGDNET_MEASURE_AUC)
+        return fail(SGDNET_ERR_ARG, "fit " + std::to_string(i) + ": type.measure 'auc' is scored one fit at a time (sgdnet_score_*): its tie-breaking "
+                                    "draws come from the caller's generator on the calling thread");
       if (s.test_rows)
         for (int64_t q = 0; q < s.n_test; ++q)
           if (s.test_rows[q] < 0 || s.test_rows[q] >= xa.n) return fail(SGDNET_ERR_ARG, "test row id out of range");
@@ -1050,9 +1138,23 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
 }
 
 int predict_or_score(const XArg& xa, const double* y, int32_t y_cols, int32_t family, const double* a0, const double* beta,
-                     int32_t L, int32_t K, double* link, double* score) {
+                     int32_t L, int32_t K, double* link, double* score, int32_t measure = SGDNET_MEASURE_DEVIANCE,
+                     sgdnet_rng* rng = nullptr) {
   if (xa.n <= 0 || xa.p <= 0 || !a0 || !beta || L <= 0 || K <= 0 || K > 32) return fail(SGDNET_ERR_ARG, "bad predict arguments");
   if (score && (!y || y_cols <= 0)) return fail(SGDNET_ERR_ARG, "score needs y");
+  std::string why;
+  if (score && !measure_ok(family, measure, why)) return fail(SGDNET_ERR_ARG, why);
+  if (score && measure == SGDNET_MEASURE_AUC) {
+    // X * beta on the device; the rank statistic (a sort with tie-breaking draws from the caller's generator, which
+    // must be called on the calling thread) on the host
+    if (!rng || rng->kind == SGDNET_RNG_SEQUENCE || (rng->kind == SGDNET_RNG_CALLBACK && !rng->unif_rand))
+      return fail(SGDNET_ERR_RNG, "type.measure 'auc' needs a generator for its tie-breaking draws (R/score.R:218)");
+    std::vector<double> eta(static_cast<size_t>(L) * xa.n);
+    const int rc = predict_or_score(xa, nullptr, 0, family, a0, beta, L, K, eta.data(), nullptr);
+    if (rc != SGDNET_OK) return rc;
+    for (int l = 0; l < L; ++l) score[l] = auc_one_lambda(eta.data() + static_cast<size_t>(l) * xa.n, y, xa.n, rng);
+    return SGDNET_OK;
+  }
   return guarded([&]() -> int {
     Engine eng;
     load_x(eng, xa, score ? y : nullptr, score ? y_cols : 1);
@@ -1063,7 +1165,7 @@ int predict_or_score(const XArg& xa, const double* y, int32_t y_cols, int32_t fa
     double* score_dev = score ? eng.arena.alloc<double>(L) : nullptr;
     eng.upload_raw();
     CK(cudaDeviceSynchronize());      // pageable uploads above (see finalize_batch)
-    eng.predict_score(family, K, L, nullptr, xa.n, a0d, bd, score != nullptr, link_dev, score_dev, eng.stream);
+    eng.predict_score(family, K, L, nullptr, xa.n, a0d, bd, score != nullptr, link_dev, score_dev, eng.stream, measure);
     CK(cudaStreamSynchronize(eng.stream));
     if (link) CK(cudaMemcpy(link, link_dev, sizeof(double) * size_t(L) * K * xa.n, cudaMemcpyDeviceToHost));
     if (score) CK(cudaMemcpy(score, score_dev, sizeof(double) * L, cudaMemcpyDeviceToHost));
@@ -1203,6 +1305,18 @@ int sgdnet_score_deviance_sparse(const int32_t* csc_i, const int32_t* csc_p, con
                                  int32_t n_lambda, int32_t n_classes, double* score) {
   if (!csc_i || !csc_p || !csc_x || !score) return fail(SGDNET_ERR_ARG, "null x or score");
   return predict_or_score(XArg{true, nullptr, csc_i, csc_p, csc_x, n, p}, y, y_cols, family, a0, beta, n_lambda, n_classes, nullptr, score);
+}
+
+int sgdnet_score_dense(const double* x, int64_t n, int64_t p, const double* y, int32_t y_cols, int32_t family, int32_t measure,
+                       const double* a0, const double* beta, int32_t n_lambda, int32_t n_classes, sgdnet_rng* rng, double* score) {
+  if (!x || !score) return fail(SGDNET_ERR_ARG, "null x or score");
+  return predict_or_score(XArg{false, x, nullptr, nullptr, nullptr, n, p}, y, y_cols, family, a0, beta, n_lambda, n_classes, nullptr, score, measure, rng);
+}
+int sgdnet_score_sparse(const int32_t* csc_i, const int32_t* csc_p, const double* csc_x, int64_t n, int64_t p, const double* y,
+                        int32_t y_cols, int32_t family, int32_t measure, const double* a0, const double* beta, int32_t n_lambda,
+                        int32_t n_classes, sgdnet_rng* rng, double* score) {
+  if (!csc_i || !csc_p || !csc_x || !score) return fail(SGDNET_ERR_ARG, "null x or score");
+  return predict_or_score(XArg{true, nullptr, csc_i, csc_p, csc_x, n, p}, y, y_cols, family, a0, beta, n_lambda, n_classes, nullptr, score, measure, rng);
 }
 
 // ---- stepping interface

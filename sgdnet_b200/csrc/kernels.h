@@ -47,11 +47,12 @@ void mt_indices_host(const MtState* src, uint32_t n, int n_epochs, uint32_t* seq
 
 // passes.cu
 cudaError_t launch_lag_scaling(FitDev* fit, Progress* prog, cudaStream_t st);
-cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, uint32_t round_id, cudaStream_t st);
+// mask_words: 32-bit words of the nonzero-coefficient bitmap the deviance pass may stage in shared memory (0: none)
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int mask_words, uint32_t round_id, cudaStream_t st);
 cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st);
 
 struct PredictArgs {
-  int32_t sparse, family, K, Ky, p, ld, n_lambda, pad_;
+  int32_t sparse, family, K, Ky, p, ld, n_lambda, measure;   // measure: SGDNET_MEASURE_* (include/sgdnet_b200.h)
   int64_t n;                 // rows to score
   const int32_t* row_ids;    // optional subset of the design's rows (NULL => 0..n-1)
   const double* xd;          // dense raw [n_total][ld]
@@ -64,7 +65,10 @@ struct PredictArgs {
   double* link;              // [L][K][n] or NULL
   double* partials;          // [blocks][L]
   double* score;             // [L] or NULL
+  const int32_t* remap;      // multinomial "class": predicted class -> id among the classes predicted anywhere, or NULL
+  uint32_t* present;         // multinomial "class": bitmap of the classes predicted anywhere (atomicOr), or NULL
 };
-cudaError_t launch_predict_score(const PredictArgs& a, double* bt_scratch /* [p][L*K] */, int blocks, cudaStream_t st);
+// transpose: fill bt_scratch from a.beta first (false when a second pass reuses it)
+cudaError_t launch_predict_score(const PredictArgs& a, double* bt_scratch /* [p][L*K] */, int blocks, cudaStream_t st, bool transpose);
 
 }  // namespace sgd

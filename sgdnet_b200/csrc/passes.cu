@@ -10,6 +10,7 @@
 //                          deviance of R/score.R:55-178, lanes across lambda so the coefficient reads are coalesced
 //
 // Algorithmic HBM bytes per loss pass: sparse 12*nnz + 16*n (row info) + 8*n*K_y; dense 8*n*ld + 8*n*K_y.
+#include "../../include/sgdnet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ double sample_loss_warp(const FitDev& f, int K, int K
 // 32 times, and the tile's 32 losses are added with one more butterfly. Partial sums: per warp in tile order, per
 // block in warp order, then the blocks in order (finish_lambda_kernel) - fixed, hence reproducible.
 __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode, int lane, int64_t warp_global,
-                                                       int64_t warp_stride) {
+                                                       int64_t warp_stride, const uint32_t* nz_smem, bool use_mask) {
   const int64_t n = f.n;
   const RowInfo* __restrict__ rows = f.rows;
   const int32_t* __restrict__ ci = f.ci;
@@ -83,8 +84,11 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
   const double* __restrict__ yt = f.yt;
   const double b0 = f.b[0];
   const int family = f.family;
-  const double inv_n = 1.0;
-  (void)inv_n;
+  // mode 0 (deviance): the bitmap of nonzero coefficients written by rescale_kernel just before this pass sits in
+  // shared memory, and a lane gathers W[j] only when it is set (the gathers - one 32-byte sector per 8-byte weight,
+  // through L1 from L2 - are what bounds this kernel; along a lasso path most weights are zero most of the time).
+  // A zero weight contributes +0.0 * v exactly as before (v is finite), so the sums keep their bits.
+  const uint32_t* __restrict__ nzm = use_mask ? nz_smem : nullptr;
   double acc = 0.0;
   const int64_t n_tiles = (n + 31) / 32;
   for (int64_t tile = warp_global; tile < n_tiles; tile += warp_stride) {
@@ -126,7 +130,10 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const double a2 = a[u] + vv[u][c] * W[jj[u][c]];
+          const int j = jj[u][c];
+          const bool live = !use_mask || ((nzm[j >> 5] >> (j & 31)) & 1u);
+          const double wj = live ? W[j] : 0.0;
+          const double a2 = a[u] + vv[u][c] * wj;
           a[u] = (c * 32 + lane < nz[u]) ? a2 : a[u];
         }
       // rows longer than 128 nonzeros (rare): the rest of the row, same association
@@ -149,7 +156,7 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
 }
 
 __global__ void __launch_bounds__(kPassThreads)
-loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode) {
+loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode, int mask_words) {
   __shared__ double wc_s[32];
   __shared__ double red_s[kPassThreads / 32];
   __shared__ double red2[2 * (kPassThreads / 32) * 32];
@@ -167,7 +174,14 @@ loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, in
   double acc = 0.0;
 
   if (f.sparse && K == 1 && !stdz) {
-    acc = loss_tiles_sparse_k1(f, mode, lane, warp_global, warp_stride);
+    extern __shared__ uint32_t nz_smem[];
+    const int words = (p + 31) / 32;
+    const bool use_mask = mode == 0 && f.nz_mask != nullptr && mask_words >= words;
+    if (use_mask) {
+      for (int i = tid; i < words; i += blockDim.x) nz_smem[i] = f.nz_mask[i];
+      __syncthreads();
+    }
+    acc = loss_tiles_sparse_k1(f, mode, lane, warp_global, warp_stride, nz_smem, use_mask);
   } else {
     // W . c per class (virtual centring), once per block
     if (stdz) {
@@ -246,26 +260,26 @@ loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, in
 }
 
 // ------------------------------------------------------------------------------------------ finish lambda
+// Rescale (src/utils.h:363-377): beta_j = w_j * y_scale / x_scale_j into the lambda's archive slot; each block also
+// leaves its share of sum_j x_center_j * beta_j (thread-strided running sums, butterfly, warps in order) for the
+// intercept, and - sparse K == 1 - the bitmap of nonzero coefficients the deviance pass uses to skip gathers of zeros.
+// Runs BEFORE the deviance pass of the same lambda.
 __global__ void __launch_bounds__(kPassThreads)
-finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int n_partials, uint32_t round_id) {
+rescale_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog) {
   __shared__ double red[(kPassThreads / 32) * 32];
-  __shared__ double xbs[32];
-  Progress& pg = *prog;
+  const Progress& pg = *prog;
   const FitDev& f = *fit;
-  if (pg.status != kLambdaDone) {
-    if (threadIdx.x == 0) publish_progress(f.mirror, pg, round_id);
-    return;
-  }
+  if (pg.status != kLambdaDone) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int K = f.K, p = f.p;
   const int li = pg.lambda_ind;
-
-  // Rescale (src/utils.h:363-377): beta_j = w_j * y_scale / x_scale_j ; a0 = b*y_scale + y_center - sum_j x_center_j beta_j
   double* __restrict__ ba = f.beta_arch + size_t(li) * p * K;
+  // features in chunks of 32 * gridDim.x ... : block b owns j = b*T + tid, stride gridDim.x*T
+  const int stride = gridDim.x * blockDim.x;
   for (int k = 0; k < K; ++k) {
     double a = 0.0;
     const double ys = f.y_scale[k];
-    for (int j = tid; j < p; j += blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + tid; j < p; j += stride) {
       const double v = f.W[size_t(k) * p + j] * (ys / f.x_scale[j]);
       ba[size_t(j) * K + k] = v;
       a += f.x_center[j] * v;
@@ -277,11 +291,38 @@ finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int 
   if (tid < K) {
     double a = 0.0;
     for (int w = 0; w < nwarps; ++w) a += red[w * 32 + tid];
-    xbs[tid] = a;
-    double b = f.b[tid];
-    if (f.fit_intercept) b = b * f.y_scale[tid] + f.y_center[tid] - a;
-    f.a0_arch[size_t(li) * K + tid] = b;
+    f.xb_partials[size_t(blockIdx.x) * K + tid] = a;
   }
+  if (f.nz_mask != nullptr) {
+    // one warp-wide ballot per 32 consecutive features
+    const int words = (p + 31) / 32;
+    for (int wd = blockIdx.x * nwarps + warp; wd < words; wd += gridDim.x * nwarps) {
+      const int j = wd * 32 + lane;
+      const uint32_t m = __ballot_sync(0xffffffffu, j < p && f.W[j] != 0.0);
+      if (lane == 0) f.nz_mask[wd] = m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPassThreads)
+finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int n_partials, uint32_t round_id) {
+  Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (pg.status != kLambdaDone) {
+    if (threadIdx.x == 0) publish_progress(f.mirror, pg, round_id);
+    return;
+  }
+  const int tid = threadIdx.x;
+  const int K = f.K;
+  const int li = pg.lambda_ind;
+  if (tid < K) {
+    double a = 0.0;
+    for (int b = 0; b < kRescaleBlocks; ++b) a += f.xb_partials[size_t(b) * K + tid];
+    double b0 = f.b[tid];
+    if (f.fit_intercept) b0 = b0 * f.y_scale[tid] + f.y_center[tid] - a;
+    f.a0_arch[size_t(li) * K + tid] = b0;
+  }
+  __syncthreads();
   if (tid == 0) {
     double dev = 0.0;
     for (int i = 0; i < n_partials; ++i) dev += f.partials[i];
@@ -294,9 +335,12 @@ finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int 
   }
 }
 
-cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, uint32_t round_id, cudaStream_t st) {
-  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 0);
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int mask_words, uint32_t round_id, cudaStream_t st) {
+  rescale_kernel<<<kRescaleBlocks, kPassThreads, 0, st>>>(fit, prog);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  loss_pass_kernel<<<blocks, kPassThreads, size_t(mask_words) * 4, st>>>(fit, prog, 0, mask_words);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   finish_lambda_kernel<<<1, kPassThreads, 0, st>>>(fit, prog, blocks, round_id);
   return cudaGetLastError();
@@ -314,7 +358,7 @@ __global__ void store_epoch_loss_kernel(FitDev* __restrict__ fit, const Progress
 }
 
 cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st) {
-  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 1);
+  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 1, 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   store_epoch_loss_kernel<<<1, 32, 0, st>>>(fit, prog, blocks);
@@ -335,16 +379,31 @@ __global__ void transpose_beta_kernel(const double* __restrict__ beta, double* _
 }
 
 // One warp per row; lanes across lambda (chunks of 32). For each class k the row is re-walked (it sits in L1).
+// Measures (R/score.R:55-178; `measure` = SGDNET_MEASURE_*): per (row, lambda) contributions, summed per warp in row
+// order, then warps and blocks in order; score_finalize_kernel divides (by n, or by K for mgaussian: R takes colMeans
+// over the responses of colSums over the samples).
+//   gaussian      deviance = mse: (eta - y)^2                    mae: |eta - y|
+//   binomial      p = 1 / (1 + exp(-eta)), y2 = y, y1 = 1 - y2   (y <- diag(2)[as.numeric(y), ])
+//                 deviance: -2 log of the clamped probability of the observed class
+//                 mse: (p + y1 - 1)^2 + (p - y2)^2   mae: |p + y1 - 1| + |p - y2|   class: y1 (p > 0.5) + y2 (p <= 0.5)
+//   multinomial   p_k = exp(eta_k) / sum_k exp(eta_k)            (R/predict.sgdnet.R:534-538: no max subtraction)
+//                 deviance: -2 log clamp(p_true)   mse: sum_k (y_k - p_k)^2   mae: sum_k |y_k - p_k|
+//                 class: 1 - y[remap(argmax_k p_k)], first maximum wins (softmax(), R/predict.sgdnet.R:104-128); remap is
+//                 the rank of the predicted class among the classes predicted anywhere (as.numeric(as.factor(...)),
+//                 R/score.R:153) - the identity unless some class is never predicted; `present` collects those classes
+//   mgaussian     deviance = mse: sum_k (eta_k - y_k)^2          mae: sum_k |eta_k - y_k|
 __global__ void __launch_bounds__(kPassThreads)
 predict_score_kernel(PredictArgs a, const double* __restrict__ bt) {
   extern __shared__ double acc_s[];   // [nwarps][L]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int L = a.n_lambda, K = a.K, Ky = a.Ky, p = a.p;
   const int LK = L * K;
+  const int measure = a.measure;
   double* my_acc = acc_s + size_t(warp) * L;
   for (int l = lane; l < L; l += 32) my_acc[l] = 0.0;
   __syncwarp();
   const double pmin = 1e-5, pmax = 1.0 - 1e-5;
+  uint32_t seen = 0;                  // multinomial "class": classes this lane predicted for some (row, lambda)
 
   const int64_t warp_global = int64_t(blockIdx.x) * nwarps + warp;
   const int64_t warp_stride = int64_t(gridDim.x) * nwarps;
@@ -366,51 +425,92 @@ predict_score_kernel(PredictArgs a, const double* __restrict__ bt) {
     for (int l0 = 0; l0 < L; l0 += 32) {
       const int l = l0 + lane;
       const bool valid = l < L;
-      double tot = 0.0, lp_true = 0.0, sq = 0.0, lp0 = 0.0;
-      unsigned cls = 0;
-      if (a.y && (a.family == kMultinomial)) cls = static_cast<unsigned>(a.y[s * Ky] + 0.5);
-      for (int k = 0; k < K; ++k) {
-        double lp = valid ? a.a0[size_t(l) * K + k] : 0.0;
-        if (valid) {
-          const double* __restrict__ col = bt + size_t(l) * K + k;
-          if (a.sparse) {
-            for (int e = 0; e < nnz; ++e) lp += cv[e] * col[size_t(ci[e]) * LK];
+      // eta_k of this row at lambda l
+      auto eta = [&](int k) {
+        double lp = a.a0[size_t(l) * K + k];
+        const double* __restrict__ col = bt + size_t(l) * K + k;
+        if (a.sparse) {
+          for (int e = 0; e < nnz; ++e) lp += cv[e] * col[size_t(ci[e]) * LK];
+        } else {
+          for (int j = 0; j < p; ++j) lp += xr[j] * col[size_t(j) * LK];
+        }
+        return lp;
+      };
+      if (!valid) continue;
+      double contrib = 0.0;
+      if (a.family == kGaussian || a.family == kBinomial) {
+        const double lp0 = eta(0);
+        if (a.link) a.link[size_t(l) * a.n + i] = lp0;
+        if (a.y) {
+          const double yv = a.y[s];
+          if (a.family == kGaussian) {
+            const double rr = lp0 - yv;
+            contrib = (measure == SGDNET_MEASURE_MAE) ? fabs(rr) : rr * rr;
           } else {
-            for (int j = 0; j < p; ++j) lp += xr[j] * col[size_t(j) * LK];
+            const double pr = 1.0 / (1.0 + sgd_exp(-lp0));
+            const double y2 = (yv > 0.5) ? 1.0 : 0.0, y1 = 1.0 - y2;
+            if (measure == SGDNET_MEASURE_DEVIANCE) {
+              const double pc = fmin(fmax(pr, pmin), pmax);
+              contrib = 2.0 * (0.0 - ((yv > 0.5) ? sgd_log(pc) : sgd_log(1.0 - pc)));
+            } else if (measure == SGDNET_MEASURE_CLASS) {
+              contrib = y1 * ((pr > 0.5) ? 1.0 : 0.0) + y2 * ((pr <= 0.5) ? 1.0 : 0.0);
+            } else {
+              const double u = (pr + y1) - 1.0, v = pr - y2;
+              contrib = (measure == SGDNET_MEASURE_MAE) ? fabs(u) + fabs(v) : u * u + v * v;
+            }
           }
+        }
+      } else if (a.family == kMGaussian) {
+        for (int k = 0; k < K; ++k) {
+          const double lp = eta(k);
           if (a.link) a.link[(size_t(l) * K + k) * a.n + i] = lp;
           if (a.y) {
-            if (a.family == kMultinomial) {
-              tot += sgd_exp(lp);
-              if (static_cast<unsigned>(k) == cls) lp_true = lp;
-            } else if (a.family == kMGaussian) {
-              const double rr = lp - a.y[s * Ky + k];
-              sq += rr * rr;
-            } else {
-              lp0 = lp;
+            const double rr = lp - a.y[s * Ky + k];
+            contrib += (measure == SGDNET_MEASURE_MAE) ? fabs(rr) : rr * rr;
+          }
+        }
+      } else {
+        const unsigned cls = a.y ? static_cast<unsigned>(a.y[s * Ky] + 0.5) : 0u;
+        double tot = 0.0, lp_true = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const double lp = eta(k);
+          if (a.link) a.link[(size_t(l) * K + k) * a.n + i] = lp;
+          tot += sgd_exp(lp);
+          if (static_cast<unsigned>(k) == cls) lp_true = lp;
+        }
+        if (a.y) {
+          if (measure == SGDNET_MEASURE_DEVIANCE) {
+            double pr = sgd_exp(lp_true) / tot;
+            pr = fmin(fmax(pr, pmin), pmax);
+            contrib = 2.0 * (0.0 - sgd_log(pr));
+          } else {
+            // a second walk over the classes, now that the normaliser is known
+            double best = 0.0;
+            int best_k = 0;
+            for (int k = 0; k < K; ++k) {
+              const double pk = sgd_exp(eta(k)) / tot;
+              const double yk = (static_cast<unsigned>(k) == cls) ? 1.0 : 0.0;
+              if (measure == SGDNET_MEASURE_MSE) contrib += (yk - pk) * (yk - pk);
+              else if (measure == SGDNET_MEASURE_MAE) contrib += fabs(yk - pk);
+              if (k == 0 || pk > best) {
+                best = pk;
+                best_k = k;
+              }
+            }
+            if (measure == SGDNET_MEASURE_CLASS) {
+              seen |= 1u << best_k;
+              const unsigned code = a.remap ? static_cast<unsigned>(a.remap[best_k]) : static_cast<unsigned>(best_k);
+              contrib = 1.0 - ((code == cls) ? 1.0 : 0.0);
             }
           }
         }
       }
-      if (valid && a.y) {
-        double contrib;
-        if (a.family == kGaussian) {
-          const double rr = lp0 - a.y[s];
-          contrib = rr * rr;
-        } else if (a.family == kBinomial) {
-          double pr = 1.0 / (1.0 + sgd_exp(-lp0));
-          pr = fmin(fmax(pr, pmin), pmax);
-          contrib = 2.0 * (0.0 - ((a.y[s] > 0.5) ? sgd_log(pr) : sgd_log(1.0 - pr)));
-        } else if (a.family == kMultinomial) {
-          double pr = sgd_exp(lp_true) / tot;
-          pr = fmin(fmax(pr, pmin), pmax);
-          contrib = 2.0 * (0.0 - sgd_log(pr));
-        } else {
-          contrib = sq;
-        }
-        my_acc[l] += contrib;
-      }
+      if (a.y) my_acc[l] += contrib;
     }
+  }
+  if (a.present != nullptr) {
+    seen = __reduce_or_sync(0xffffffffu, seen);
+    if (lane == 0 && seen != 0u) atomicOr(a.present, seen);
   }
   __syncthreads();
   if (a.partials) {
@@ -430,10 +530,13 @@ __global__ void score_finalize_kernel(PredictArgs a, int blocks) {
   }
 }
 
-cudaError_t launch_predict_score(const PredictArgs& a, double* bt_scratch, int blocks, cudaStream_t st) {
-  transpose_beta_kernel<<<296, 256, 0, st>>>(a.beta, bt_scratch, a.n_lambda, a.p, a.K);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+cudaError_t launch_predict_score(const PredictArgs& a, double* bt_scratch, int blocks, cudaStream_t st, bool transpose) {
+  cudaError_t e = cudaSuccess;
+  if (transpose) {
+    transpose_beta_kernel<<<296, 256, 0, st>>>(a.beta, bt_scratch, a.n_lambda, a.p, a.K);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   const size_t smem = sizeof(double) * (kPassThreads / 32) * a.n_lambda;
   predict_score_kernel<<<blocks, kPassThreads, smem, st>>>(a, bt_scratch);
   e = cudaGetLastError();

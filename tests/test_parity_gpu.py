@@ -215,7 +215,23 @@ from score_cases import SCORE_CASES, check_backend_against_fixture  # noqa: E402
 def test_predict_and_score_match_the_r_rendering(cuda, name):
     """predict + score against tests/golden/score_fixture.npz: R/score.R and R/predict.sgdnet.R rendered in numpy
     (tests/r_score.py) on the reference build's coefficients - a pin that does not pass through the oracle."""
-    assert "deviance" in check_backend_against_fixture(cuda, name)
+    assert set(check_backend_against_fixture(cuda, name)) == set(SCORE_CASES[name][2])
+
+
+def test_class_measure_when_a_class_is_never_predicted_on_the_device(cuda):
+    """the two-pass path of predict_score (engine.cu): classes predicted anywhere -> ids, R/score.R:153."""
+    import r_score
+    from score_cases import raw_coefficients
+    rng = np.random.default_rng(3)
+    n, p, K, L = 60, 4, 3, 3
+    x = rng.normal(size=(n, p))
+    y = np.arange(n) % K
+    a0 = np.zeros((K, L))
+    a0[1, :] = -50.0
+    beta = [rng.normal(size=(p, L)) * (0.0 if k == 1 else 1.0) for k in range(K)]
+    a0r, br = raw_coefficients("multinomial", a0, beta)
+    got = cuda.score(x, y.astype(float).reshape(-1, 1), 2, "class", a0r, br)
+    np.testing.assert_allclose(got, r_score.score("multinomial", a0, beta, x, y, "class"), rtol=1e-12)
 
 
 def test_cv_batch_matches_sequential_oracle(cuda, oracle):
@@ -229,6 +245,20 @@ def test_cv_batch_matches_sequential_oracle(cuda, oracle):
     for cg, cr in zip(g.cv_raw, r.cv_raw):
         rel_close(cg, cr, what="cv_raw")
     assert g.alpha_min == r.alpha_min and g.lambda_min == r.lambda_min and g.lambda_1se == r.lambda_1se
+
+
+@pytest.mark.parametrize("measure", ["mse", "mae", "class"])
+def test_cv_other_measures_match_the_oracle(cuda, oracle, measure):
+    """type.measure other than deviance through the batch call (scored on each fit's stream as it finishes)."""
+    x, y = synth.binomial_sparse(1200, 200, 10, seed=33)
+    foldid = (np.random.Generator(np.random.PCG64(2)).permutation(1200) % 4) + 1
+    kw = dict(family="binomial", alpha=[0.3, 1.0], foldid=foldid, nlambda=6, standardize=False, maxit=60, seed=700,
+              type_measure=measure)
+    g = sg.cv_sgdnet(x, y, backend=cuda, **kw)
+    r = sg.cv_sgdnet(x, y, backend=oracle, batched=False, **kw)
+    for cg, cr in zip(g.cv_raw, r.cv_raw):
+        rel_close(cg, cr, rtol=1e-9, what="cv_raw " + measure)
+    assert g.name == r.name and g.lambda_min == r.lambda_min
 
 
 # ---------------------------------------------------------------- against the reference's own compiled code
