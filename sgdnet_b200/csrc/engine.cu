@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -28,6 +29,7 @@
 #include "../../include/sgdnet_b200.h"
 #include "host_setup.h"
 #include "kernels.h"
+#include "setup.h"
 
 namespace sgd {
 
@@ -147,6 +149,22 @@ struct DeviceDesign {
   const int32_t* ci = nullptr;
   const double* cv = nullptr;
   const double *c = nullptr, *x_center = nullptr, *x_scale = nullptr;
+  const int32_t* local = nullptr;     // sparse row subset: source row -> position in this view, or -1 (X^T y walks the CSC)
+};
+
+// The caller's matrix on the device: the dgCMatrix as given (CSC) plus its padded CSR (setup.cu), or the numeric
+// matrix as given (column-major).
+struct RawInput {
+  bool sparse = false;
+  int64_t n = 0, nnz = 0;
+  int32_t p = 0;
+  const int32_t *csc_i = nullptr, *csc_p = nullptr;
+  const double* csc_x = nullptr;
+  const RowInfo* rows = nullptr;
+  const int32_t* ci = nullptr;
+  const double* cv = nullptr;
+  int64_t n_entries = 0;
+  const double* dense_cm = nullptr;
 };
 
 enum class Variant { Dense, SparseK1, SparseGeneric };
@@ -217,7 +235,8 @@ struct FitJob {
 
 struct Engine {
   Arena arena;
-  RawX raw;
+  RawInput raw;
+  std::mutex xt_mutex;                // X^T y requests from the plan threads are served one at a time
   std::vector<double> y_cm;           // caller's y, n x Ky column-major
   int Ky = 1;
   std::map<std::pair<const int32_t*, int>, std::pair<std::shared_ptr<HostDesign>, DeviceDesign>> designs;
@@ -261,27 +280,155 @@ struct Engine {
     if (stream) cudaStreamDestroy(stream);
   }
 
-  // ---------------------------------------------------------------------------------- designs
+  // ---------------------------------------------------------------------------------- input and designs (device)
+  template <typename T>
+  T download_scalar(const T* dev) {
+    T v;
+    CK(cudaMemcpyAsync(&v, dev, sizeof(T), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return v;
+  }
+  // pageable host memory -> device, ordered on `stream` (the DMA of a synchronous cudaMemcpy may still be in flight
+  // when it returns, on the legacy stream; this one is followed by work on `stream`)
+  template <typename T>
+  T* upload_on_stream(const T* src, size_t count) {
+    T* p = arena.alloc<T>(count, false);
+    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return p;
+  }
+
+  void load_sparse(const int32_t* ci_, const int32_t* cp_, const double* cx_, int64_t n_, int64_t p_) {
+    PhaseTimer pt;
+    raw.sparse = true;
+    raw.n = n_;
+    raw.p = static_cast<int32_t>(p_);
+    raw.nnz = cp_[p_];
+    raw.csc_i = upload_on_stream(ci_, static_cast<size_t>(raw.nnz));
+    raw.csc_p = upload_on_stream(cp_, static_cast<size_t>(p_) + 1);
+    raw.csc_x = upload_on_stream(cx_, static_cast<size_t>(raw.nnz));
+    pt.lap("CSC upload (issued)");
+    // CSC -> padded CSR on the device (AdaptiveTranspose, src/utils.h:276-281)
+    int32_t* counts = arena.alloc<int32_t>(static_cast<size_t>(raw.n), false);
+    int32_t* cursor = arena.alloc<int32_t>(static_cast<size_t>(raw.n), false);
+    int64_t* block_tot = arena.alloc<int64_t>(static_cast<size_t>(csc_to_csr_scan_blocks(raw.n)), false);
+    int64_t* totals = arena.alloc<int64_t>(2, false);
+    CK(csc_to_csr_counts(raw.csc_i, raw.nnz, raw.n, counts, block_tot, totals, stream));
+    int64_t tot[2];
+    CK(cudaMemcpyAsync(tot, totals, sizeof(tot), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    raw.n_entries = tot[0] + 4;
+    RowInfo* rows = arena.alloc<RowInfo>(static_cast<size_t>(raw.n), false);
+    int32_t* ci = arena.alloc<int32_t>(static_cast<size_t>(raw.n_entries), false);
+    double* cv = arena.alloc<double>(static_cast<size_t>(raw.n_entries), false);
+    CK(cudaMemsetAsync(ci + tot[0], 0, 4 * sizeof(int32_t), stream));
+    CK(cudaMemsetAsync(cv + tot[0], 0, 4 * sizeof(double), stream));
+    int32_t* sk = nullptr;
+    double* sv = nullptr;
+    if (tot[1] > 128) {      // rows too long for the in-register sort use scratch of the same size
+      sk = arena.alloc<int32_t>(static_cast<size_t>(raw.n_entries), false);
+      sv = arena.alloc<double>(static_cast<size_t>(raw.n_entries), false);
+    }
+    CK(csc_to_csr_fill(raw.csc_i, raw.csc_p, raw.csc_x, raw.n, raw.p, counts, block_tot, rows, cursor, ci, cv, sk, sv, stream));
+    raw.rows = rows;
+    raw.ci = ci;
+    raw.cv = cv;
+    if (PhaseTimer().on) CK(cudaStreamSynchronize(stream));
+    pt.lap("CSC -> CSR (device)");
+  }
+
+  void load_dense(const double* x, int64_t n_, int64_t p_) {
+    PhaseTimer pt;
+    raw.sparse = false;
+    raw.n = n_;
+    raw.p = static_cast<int32_t>(p_);
+    raw.dense_cm = upload_on_stream(x, static_cast<size_t>(n_) * p_);
+    pt.lap("dense upload (issued)");
+  }
+
   std::pair<std::shared_ptr<HostDesign>, DeviceDesign> get_design(const int32_t* rows, int64_t n_rows, bool standardize) {
     auto key = std::make_pair(rows, standardize ? 1 : 0);
     auto it = designs.find(key);
     if (it != designs.end()) return it->second;
     auto hd = std::make_shared<HostDesign>();
     PhaseTimer pt;
-    hd->build(raw, rows, n_rows, standardize);
-    pt.lap("design build (host)");
+    hd->sparse = raw.sparse;
+    hd->standardized = standardize;
+    hd->n = rows ? n_rows : raw.n;
+    hd->p = raw.p;
+    hd->ld = (raw.p + 1) & ~1;
+    const int64_t n = hd->n;
+    const int32_t p = raw.p;
     DeviceDesign dd;
-    if (hd->sparse) {
-      dd.rows = arena.upload_from(hd->rows_v, static_cast<size_t>(hd->n));
-      dd.ci = arena.upload_from(hd->ci_v, hd->n_entries);
-      dd.cv = arena.upload_from(hd->cv_v, hd->n_entries);
-    } else {
-      dd.xd = arena.upload(hd->xd);
+    const int32_t* subset_dev = rows ? upload_on_stream(rows, static_cast<size_t>(n_rows)) : nullptr;
+    double* x_center = arena.alloc<double>(p);                         // zero
+    double* x_scale = arena.alloc<double>(p, false);
+    double* c = arena.alloc<double>(p);                                // zero
+    {
+      std::vector<double> ones(p, 1.0);
+      CK(cudaMemcpyAsync(x_scale, ones.data(), sizeof(double) * p, cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));                              // `ones` goes away
     }
-    pt.lap("design upload");
-    dd.c = arena.upload(hd->c);
-    dd.x_center = arena.upload(hd->x_center);
-    dd.x_scale = arena.upload(hd->x_scale);
+    unsigned long long* norm_bits = arena.alloc<unsigned long long>(1, false);
+    if (raw.sparse) {
+      int32_t* local = nullptr;
+      if (rows) {
+        local = arena.alloc<int32_t>(static_cast<size_t>(raw.n), false);
+        CK(subset_local(subset_dev, n, raw.n, local, stream));
+      }
+      dd.local = local;
+      if (standardize) CK(sparse_col_stats(raw.csc_i, raw.csc_p, raw.csc_x, p, local, n, x_center, x_scale, c, stream));
+      if (!rows && !standardize) {
+        dd.rows = raw.rows;       // all rows, values as given: the raw CSR is the design
+        dd.ci = raw.ci;
+        dd.cv = raw.cv;
+      } else {
+        int32_t* counts = arena.alloc<int32_t>(static_cast<size_t>(n), false);
+        int32_t* cursor = arena.alloc<int32_t>(static_cast<size_t>(n), false);
+        int64_t* block_tot = arena.alloc<int64_t>(static_cast<size_t>(csc_to_csr_scan_blocks(n)), false);
+        int64_t* totals = arena.alloc<int64_t>(2, false);
+        CK(subset_counts(raw.rows, subset_dev, n, counts, block_tot, totals, stream));
+        const int64_t entries = download_scalar(totals);
+        RowInfo* drows = arena.alloc<RowInfo>(static_cast<size_t>(n), false);
+        int32_t* dci = arena.alloc<int32_t>(static_cast<size_t>(entries) + 4, false);
+        double* dcv = arena.alloc<double>(static_cast<size_t>(entries) + 4, false);
+        CK(cudaMemsetAsync(dci + entries, 0, 4 * sizeof(int32_t), stream));
+        CK(cudaMemsetAsync(dcv + entries, 0, 4 * sizeof(double), stream));
+        CK(gather_rows(raw.rows, raw.ci, raw.cv, subset_dev, n, counts, block_tot, drows, cursor, dci, dcv,
+                       standardize ? x_scale : nullptr, stream));
+        dd.rows = drows;
+        dd.ci = dci;
+        dd.cv = dcv;
+      }
+      CK(sparse_norm_max(dd.rows, dd.ci, dd.cv, n, p, standardize ? c : nullptr, norm_bits, stream));
+    } else {
+      double* xd = arena.alloc<double>(static_cast<size_t>(n) * hd->ld, false);
+      CK(dense_design(raw.dense_cm, raw.n, p, subset_dev, n, hd->ld, standardize, x_center, x_scale, xd, norm_bits, stream));
+      dd.xd = xd;
+    }
+    const unsigned long long bits = download_scalar(norm_bits);
+    std::memcpy(&hd->norm_max, &bits, sizeof(double));
+    dd.c = c;
+    dd.x_center = x_center;
+    dd.x_scale = x_scale;
+    pt.lap("design (device)");
+    // X^T y for LambdaMax: asked for by the plan (possibly from a helper thread), answered by the device
+    const DeviceDesign ddc = dd;
+    const int64_t n_view = n;
+    const int32_t ld = hd->ld;
+    const bool std_ = standardize;
+    hd->xt_times_fn = [this, ddc, n_view, p, ld, std_](const std::vector<double>& ymap, int m, std::vector<double>& out) {
+      std::lock_guard<std::mutex> lock(xt_mutex);
+      out.assign(static_cast<size_t>(m) * p, 0.0);
+      double* ymap_dev = arena.alloc<double>(ymap.size(), false);
+      double* out_dev = arena.alloc<double>(out.size(), false);
+      CK(cudaMemcpyAsync(ymap_dev, ymap.data(), sizeof(double) * ymap.size(), cudaMemcpyHostToDevice, stream));
+      if (raw.sparse)
+        CK(sparse_xt_times(raw.csc_i, raw.csc_p, raw.csc_x, p, ddc.local, n_view, std_ ? ddc.x_scale : nullptr, ymap_dev, m, out_dev, stream));
+      else
+        CK(dense_xt_times(ddc.xd, n_view, p, ld, ymap_dev, m, out_dev, stream));
+      CK(cudaMemcpyAsync(out.data(), out_dev, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+    };
     designs[key] = {hd, dd};
     return {hd, dd};
   }
@@ -962,9 +1109,8 @@ struct XArg {
 
 void load_x(Engine& eng, const XArg& xa, const double* y, int32_t y_cols) {
   PhaseTimer pt;
-  if (xa.sparse) eng.raw.from_csc(xa.ci, xa.cp, xa.cx, xa.n, xa.p);
-  else eng.raw.from_dense(xa.x, xa.n, xa.p);
-  pt.lap("CSC -> CSR");
+  if (xa.sparse) eng.load_sparse(xa.ci, xa.cp, xa.cx, xa.n, xa.p);
+  else eng.load_dense(xa.x, xa.n, xa.p);
   eng.Ky = y_cols;
   if (y) eng.y_cm.assign(y, y + static_cast<size_t>(xa.n) * y_cols);
 }
@@ -1334,7 +1480,6 @@ static int session_create(const XArg& xa, const double* y, int32_t y_cols, const
     std::string err = s->eng.add_fit(nullptr, xa.n, *control, &placeholder, nullptr, 0);
     if (!err.empty()) return fail(SGDNET_ERR_ARG, err);
     s->eng.finalize_batch();
-    s->eng.raw.release_rows();
     *out = s.release();
     return SGDNET_OK;
   });

@@ -9,287 +9,6 @@
 
 namespace sgd {
 
-// ------------------------------------------------------------------------------------------ RawX
-void RawX::from_dense(const double* x, int64_t n_, int64_t p_) {
-  sparse = false;
-  n = n_;
-  p = static_cast<int32_t>(p_);
-  dense_cm = x;
-}
-
-// Runs body(k, K) on K host threads (K = 1 runs inline). Used only where the result does not depend on K.
-template <typename F>
-static void parallel_blocks(int K, F&& body) {
-  if (K <= 1) {
-    body(0, 1);
-    return;
-  }
-  std::vector<std::thread> th;
-  th.reserve(K);
-  for (int k = 0; k < K; ++k) th.emplace_back([&body, k, K] { body(k, K); });
-  for (auto& t : th) t.join();
-}
-
-static int host_threads(int64_t work) {
-  if (work < (int64_t(1) << 22)) return 1;
-  const unsigned hc = std::thread::hardware_concurrency();
-  return static_cast<int>(std::max(1u, std::min(16u, hc)));
-}
-
-// CSC -> padded CSR (the reference's AdaptiveTranspose, src/utils.h:276-281). Row counts come from per-thread
-// histograms over slices of the entry array; the fill walks, for one block of rows at a time (small enough that its
-// output stays cache-resident), every column's ascending row-index run restricted to the block - column ids therefore
-// stay ascending inside every row and the result is the same for any thread count.
-void RawX::from_csc(const int32_t* ci_, const int32_t* cp_, const double* cx_, int64_t n_, int64_t p_) {
-  sparse = true;
-  n = n_;
-  p = static_cast<int32_t>(p_);
-  csc_i = ci_;
-  csc_p = cp_;
-  csc_x = cx_;
-  const int64_t nnz = cp_[p_];
-  const int K = host_threads(nnz);
-  // ---- counts
-  std::vector<std::vector<int32_t>> hist(K);
-  parallel_blocks(K, [&](int k, int Kt) {
-    std::vector<int32_t>& h = hist[k];
-    h.assign(n, 0);
-    for (int64_t e = nnz * k / Kt; e < nnz * (k + 1) / Kt; ++e) ++h[ci_[e]];
-  });
-  rows.resize(n);
-  int64_t cursor = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    int32_t c = 0;
-    for (int k = 0; k < K; ++k) c += hist[k][i];
-    rows[i].start = cursor;
-    rows[i].nnz = c;
-    rows[i].pad_ = 0;
-    cursor += (c + 3) & ~3;
-  }
-  hist.clear();
-  ci.allocate(static_cast<size_t>(cursor) + 4);
-  cv.allocate(static_cast<size_t>(cursor) + 4);
-  for (int q = 0; q < 4; ++q) {
-    ci[cursor + q] = 0;
-    cv[cursor + q] = 0.0;
-  }
-  // ---- fill, one block of rows at a time
-  const int64_t block = 16384;
-  const int64_t n_blocks = (n + block - 1) / block;
-  std::atomic<int64_t> next{0};
-  parallel_blocks(K, [&](int, int) {
-    std::vector<int64_t> fill(block);
-    for (;;) {
-      const int64_t bl = next.fetch_add(1);
-      if (bl >= n_blocks) break;
-      const int64_t r0 = bl * block, r1 = std::min(n, r0 + block);
-      for (int64_t i = r0; i < r1; ++i) fill[i - r0] = rows[i].start;
-      for (int64_t j = 0; j < p_; ++j) {          // ascending j => ascending column ids inside every row
-        int64_t lo = cp_[j], hi = cp_[j + 1];
-        if (n_blocks > 1) {
-          lo = std::lower_bound(ci_ + lo, ci_ + hi, static_cast<int32_t>(r0)) - ci_;
-          hi = std::lower_bound(ci_ + lo, ci_ + hi, static_cast<int32_t>(r1)) - ci_;
-        }
-        for (int64_t e = lo; e < hi; ++e) {
-          const int64_t dst = fill[ci_[e] - r0]++;
-          ci[dst] = static_cast<int32_t>(j);
-          cv[dst] = cx_[e];
-        }
-      }
-      for (int64_t i = r0; i < r1; ++i)           // the (at most 3) pad entries of every row
-        for (int64_t q = rows[i].start + rows[i].nnz; q < rows[i].start + ((rows[i].nnz + 3) & ~3); ++q) {
-          ci[q] = 0;
-          cv[q] = 0.0;
-        }
-    }
-  });
-}
-
-// ------------------------------------------------------------------------------------------ HostDesign
-void HostDesign::build(const RawX& raw, const int32_t* subset, int64_t n_rows, bool standardize) {
-  sparse = raw.sparse;
-  standardized = standardize;
-  n = subset ? n_rows : raw.n;
-  p = raw.p;
-  ld = (p + 1) & ~1;
-  x_center.assign(p, 0.0);
-  x_scale.assign(p, 1.0);
-  c.assign(p, 0.0);
-  const double nd = static_cast<double>(n);
-  auto src_row = [&](int64_t i) -> int64_t { return subset ? subset[i] : i; };
-
-  if (!sparse) {
-    xd.assign(static_cast<size_t>(n) * ld, 0.0);
-    for (int32_t j = 0; j < p; ++j) {
-      const double* col = raw.dense_cm + static_cast<size_t>(j) * raw.n;
-      for (int64_t i = 0; i < n; ++i) xd[static_cast<size_t>(i) * ld + j] = col[src_row(i)];
-    }
-    if (standardize) {
-      // Mean, StandardDeviation, Standardize (src/math.h:66-79, 114-130, 139-150): centre and scale in place
-      for (int32_t j = 0; j < p; ++j) {
-        double total = 0.0;
-        for (int64_t i = 0; i < n; ++i) total += xd[static_cast<size_t>(i) * ld + j];
-        const double mean = total / nd;
-        double ss = 0.0;
-        for (int64_t i = 0; i < n; ++i) {
-          const double dev = xd[static_cast<size_t>(i) * ld + j] - mean;
-          ss += dev * dev;
-        }
-        const double var = ss / nd;
-        const double sd = (var == 0.0) ? 1.0 : std::sqrt(var);
-        x_center[j] = mean;
-        x_scale[j] = sd;
-        for (int64_t i = 0; i < n; ++i) {
-          double& v = xd[static_cast<size_t>(i) * ld + j];
-          v = (v - mean) / sd;
-        }
-      }
-    }
-    norm_max = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-      double sq = 0.0;
-      const double* row = &xd[static_cast<size_t>(i) * ld];
-      for (int32_t j = 0; j < p; ++j) sq += row[j] * row[j];
-      norm_max = std::max(norm_max, sq);
-    }
-    max_nnz = p;
-    return;
-  }
-
-  // sparse: padded CSR of the selected rows
-  raw_src = &raw;
-  subset_src = subset;
-  max_nnz = 0;
-  if (!subset && !standardize) {
-    // all rows, values as given: the RawX arrays are the design (no copy)
-    rows_v = raw.rows.data();
-    ci_v = raw.ci.data();
-    cv_v = raw.cv.data();
-    n_entries = raw.ci.size();
-    for (int64_t i = 0; i < n; ++i) max_nnz = std::max(max_nnz, rows_v[i].nnz);
-  } else {
-    rows.resize(n);
-    int64_t cursor = 0;
-    for (int64_t i = 0; i < n; ++i) {
-      const int64_t r = src_row(i);
-      const int32_t nnz = raw.rows[r].nnz;
-      rows[i].start = cursor;
-      rows[i].nnz = nnz;
-      rows[i].pad_ = 0;
-      cursor += (nnz + 3) & ~3;
-      max_nnz = std::max(max_nnz, nnz);
-    }
-    ci.assign(static_cast<size_t>(cursor) + 4, 0);
-    cv.assign(static_cast<size_t>(cursor) + 4, 0.0);
-    parallel_blocks(host_threads(cursor), [&](int k, int Kt) {
-      for (int64_t i = n * k / Kt; i < n * (k + 1) / Kt; ++i) {
-        const int64_t b = raw.rows[src_row(i)].start;
-        std::memcpy(&ci[rows[i].start], &raw.ci[b], sizeof(int32_t) * rows[i].nnz);
-        std::memcpy(&cv[rows[i].start], &raw.cv[b], sizeof(double) * rows[i].nnz);
-      }
-    });
-    rows_v = rows.data();
-    ci_v = ci.data();
-    cv_v = cv.data();
-    n_entries = ci.size();
-  }
-  if (standardize) {
-    // sparse Mean / StandardDeviation (src/math.h:66-79, 89-112): per-column running sums in ascending row order;
-    // then scale only (src/utils.h:118-120), centring stays virtual through c = center/scale (src/sgdnet.cpp:150)
-    std::vector<double> total(p, 0.0), var(p, 0.0);
-    std::vector<int64_t> count(p, 0);
-    for (int64_t i = 0; i < n; ++i)
-      for (int32_t e = 0; e < rows[i].nnz; ++e) {
-        const int32_t j = ci[rows[i].start + e];
-        total[j] += cv[rows[i].start + e];
-        ++count[j];
-      }
-    for (int32_t j = 0; j < p; ++j) x_center[j] = total[j] / nd;
-    for (int64_t i = 0; i < n; ++i)
-      for (int32_t e = 0; e < rows[i].nnz; ++e) {
-        const int32_t j = ci[rows[i].start + e];
-        var[j] += std::pow(cv[rows[i].start + e] - x_center[j], 2) / nd;
-      }
-    for (int32_t j = 0; j < p; ++j) {
-      const int64_t zeros = n - count[j];
-      var[j] += static_cast<double>(zeros) * x_center[j] * x_center[j] / nd;
-      x_scale[j] = (var[j] == 0.0) ? 1.0 : std::sqrt(var[j]);
-    }
-    for (int64_t i = 0; i < n; ++i)
-      for (int32_t e = 0; e < rows[i].nnz; ++e) cv[rows[i].start + e] /= x_scale[ci[rows[i].start + e]];
-    for (int32_t j = 0; j < p; ++j) c[j] = x_center[j] / x_scale[j];
-  }
-  // ColNormsMax (src/utils.h:60-85): ||x_s - c||^2 over ALL features when centring is virtual
-  const int Kn = host_threads(standardize ? int64_t(n) * p : static_cast<int64_t>(n_entries));
-  std::vector<double> part(Kn, 0.0);
-  parallel_blocks(Kn, [&](int k, int Kt) {     // a max over rows: the same for any split
-    double best = 0.0;
-    for (int64_t i = n * k / Kt; i < n * (k + 1) / Kt; ++i) {
-      double sq = 0.0;
-      if (standardize) {
-        int32_t e = 0;
-        const int64_t b = rows_v[i].start;
-        for (int32_t j = 0; j < p; ++j) {
-          double v = 0.0;
-          if (e < rows_v[i].nnz && ci_v[b + e] == j) v = cv_v[b + e++];
-          const double dev = v - c[j];
-          sq += dev * dev;
-        }
-      } else {
-        const double* rv = cv_v + rows_v[i].start;
-        for (int32_t e = 0; e < rows_v[i].nnz; ++e) sq += rv[e] * rv[e];
-      }
-      best = std::max(best, sq);
-    }
-    part[k] = best;
-  });
-  norm_max = 0.0;
-  for (double v : part) norm_max = std::max(norm_max, v);
-}
-
-void HostDesign::xt_times(const std::vector<double>& ymap, int m, std::vector<double>& out) const {
-  out.assign(static_cast<size_t>(m) * p, 0.0);
-  for (int col = 0; col < m; ++col) {
-    const double* yc = &ymap[static_cast<size_t>(col) * n];
-    double* oc = &out[static_cast<size_t>(col) * p];
-    if (sparse && raw_src && raw_src->csc_p) {
-      // column by column over the caller's CSC (rows ascending inside a column): the same products added in the
-      // same order as the row-major walk below, but columns are independent, so they are spread over host threads
-      const RawX& raw = *raw_src;
-      std::vector<int32_t> local;               // source row -> position in this view (or -1)
-      if (subset_src) {
-        local.assign(raw.n, -1);
-        for (int64_t i = 0; i < n; ++i) local[subset_src[i]] = static_cast<int32_t>(i);
-      }
-      const int32_t* loc = subset_src ? local.data() : nullptr;
-      parallel_blocks(host_threads(raw.csc_p[p]), [&](int k, int Kt) {
-        for (int64_t j = int64_t(p) * k / Kt; j < int64_t(p) * (k + 1) / Kt; ++j) {
-          double acc = 0.0;
-          const double sc = x_scale[j];
-          for (int64_t e = raw.csc_p[j]; e < raw.csc_p[j + 1]; ++e) {
-            const int32_t src = raw.csc_i[e];
-            const int32_t i = loc ? loc[src] : src;
-            if (i < 0) continue;
-            const double v = standardized ? raw.csc_x[e] / sc : raw.csc_x[e];
-            acc += v * yc[i];
-          }
-          oc[j] = acc;
-        }
-      });
-    } else if (sparse) {
-      for (int64_t i = 0; i < n; ++i) {
-        const int64_t b = rows_v[i].start;
-        for (int32_t e = 0; e < rows_v[i].nnz; ++e) oc[ci_v[b + e]] += cv_v[b + e] * yc[i];
-      }
-    } else {
-      for (int64_t i = 0; i < n; ++i) {
-        const double* row = &xd[static_cast<size_t>(i) * ld];
-        for (int32_t j = 0; j < p; ++j) oc[j] += row[j] * yc[i];
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------ FitPlan
 namespace {
 

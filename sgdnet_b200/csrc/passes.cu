@@ -155,7 +155,7 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
   return acc;
 }
 
-__global__ void __launch_bounds__(kPassThreads)
+__global__ void __launch_bounds__(kPassThreads, 3)
 loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode, int mask_words) {
   __shared__ double wc_s[32];
   __shared__ double red_s[kPassThreads / 32];
@@ -438,12 +438,12 @@ predict_score_kernel(PredictArgs a, const double* __restrict__ bt) {
       };
       if (!valid) continue;
       double contrib = 0.0;
-      if (a.family == kGaussian || a.family == kBinomial) {
+      if (K == 1) {
         const double lp0 = eta(0);
         if (a.link) a.link[size_t(l) * a.n + i] = lp0;
         if (a.y) {
           const double yv = a.y[s];
-          if (a.family == kGaussian) {
+          if (a.family != kBinomial) {
             const double rr = lp0 - yv;
             contrib = (measure == SGDNET_MEASURE_MAE) ? fabs(rr) : rr * rr;
           } else {
@@ -460,7 +460,7 @@ predict_score_kernel(PredictArgs a, const double* __restrict__ bt) {
             }
           }
         }
-      } else if (a.family == kMGaussian) {
+      } else if (a.family != kMultinomial || !a.y) {      // mgaussian, and plain prediction for any K > 1
         for (int k = 0; k < K; ++k) {
           const double lp = eta(k);
           if (a.link) a.link[(size_t(l) * K + k) * a.n + i] = lp;
