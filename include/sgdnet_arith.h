@@ -14,7 +14,10 @@
  *  2. reductions inside the solver loop have a fixed association order (documented where they are used:
  *     sgdnet_b200/csrc/saga_*.cu, DESIGN.md section "arithmetic"): a dense dot product over p features is 256
  *     interleaved running sums (feature j -> sum j mod 256, ascending j), each group of 32 consecutive sums is
- *     combined by the xor-butterfly 16,8,4,2,1, the 8 group results are added in ascending order; a sparse row dot
+ *     combined by the xor-butterfly 16,8,4,2,1, the 8 group results are added in ascending order; from
+ *     SGD_WIDE_P = 512 features on the same scheme runs eight blocks wide: 2048 interleaved running sums, butterfly
+ *     per 32, the 8 group results of each block of 256 sums added in ascending order, then the 8 block sums added
+ *     in ascending order (one block per CTA of the solver's thread-block cluster); a sparse row dot
  *     product is 32 interleaved running sums over the row's nonzero positions, combined by the same butterfly; a
  *     sum over K <= 32 classes is the butterfly over 32 slots padded with zeros.
  *
@@ -27,6 +30,8 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+
+#define SGD_WIDE_P 512   /* dense designs with at least this many features use the eight-block dot product */
 
 #if defined(__CUDACC__)
 #define SGD_HD __host__ __device__ __forceinline__

@@ -84,6 +84,22 @@ inline double dot_dense(const double* a, int64_t sa, const double* b, int64_t p)
   return total;
 }
 
+/* wide dense dot product (p >= SGD_WIDE_P, include/sgdnet_arith.h item 2): 2048 interleaved running sums (feature j ->
+   sum j mod 2048, ascending j), butterfly per 32 consecutive sums, the 8 results of each block of 256 sums added in
+   ascending order, the 8 block sums added in ascending order */
+inline double dot_dense_wide(const double* a, int64_t sa, const double* b, int64_t p) {
+  static thread_local double chain[2048];
+  for (int i = 0; i < 2048; ++i) chain[i] = 0.0;
+  for (int64_t j = 0; j < p; ++j) chain[j & 2047] += a[j * sa] * b[j];
+  double total = 0.0;
+  for (int c = 0; c < 8; ++c) {
+    double block = 0.0;
+    for (int g = 0; g < 8; ++g) block += butterfly32(chain + 256 * c + 32 * g);
+    total += block;
+  }
+  return total;
+}
+
 /* sparse row dot product sum_e val[e] * w[idx[e]*sw]: 32 interleaved running sums over positions, butterfly */
 inline double dot_sparse(const double* val, const int32_t* idx, int64_t nnz, const double* w, int64_t sw) {
   if (!g_arith) {
@@ -550,7 +566,7 @@ int saga_dense(const Model& m, const Design& d, const std::vector<double>& c, co
       if (!draw_index(rng, static_cast<uint32_t>(n), &s)) return SGDNET_ERR_RNG;
       const double* xs = &d.dense[static_cast<size_t>(s) * p];
 
-      for (int k = 0; k < K; ++k) lp[k] = dot_dense(&st.W[k], K, xs, p);
+      for (int k = 0; k < K; ++k) lp[k] = (g_arith && p >= SGD_WIDE_P) ? dot_dense_wide(&st.W[k], K, xs, p) : dot_dense(&st.W[k], K, xs, p);
       for (int k = 0; k < K; ++k) lp[k] = lp[k] * wscale + st.b[k];
 
       family_gradient(m, lp.data(), yt.data(), s, g.data());

@@ -220,6 +220,7 @@ struct FitJob {
   int loss_blocks = 1;
   int mask_words = 0;                 // sparse K == 1: words of the nonzero-coefficient bitmap (0: p too large for it)
   size_t dense_smem = 0;
+  bool dense_cluster = false;         // wide dense design: the cluster kernel (saga_dense_cluster.cu)
   double seconds_solver = 0.0, seconds_dev = 0.0;
   uint64_t launches = 0;
   double t_submit = 0.0, t_finish = 0.0;
@@ -248,6 +249,7 @@ struct Engine {
   bool no_overlap = std::getenv("SGDNET_NO_PREP_OVERLAP") != nullptr;  // prepare a launch only when it is due
   double seconds_setup = 0.0;
   double t_begin = 0.0, t_run = 0.0;
+  size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set aside for persisting lines (0: not available / switched off)
   // raw design for scoring (device)
   DeviceDesign raw_dev;
   bool raw_uploaded = false;
@@ -263,6 +265,16 @@ struct Engine {
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    if (std::getenv("SGDNET_NO_L2_PERSIST") == nullptr) {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev_id);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev_id);
+      if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist)) == cudaSuccess) {
+        l2_persist_bytes = static_cast<size_t>(max_persist);
+        l2_window_max = static_cast<size_t>(max_window);
+      }
+      (void)cudaGetLastError();
+    }
     t_begin = now_s();
   }
   ~Engine() {
@@ -559,7 +571,12 @@ struct Engine {
     const int mask_words = (p + 31) / 32;
     job.mask_words = (job.variant == Variant::SparseK1 && mask_words * 4 <= 40 * 1024) ? mask_words : 0;
     f.nz_mask = job.mask_words ? arena.alloc<uint32_t>(mask_words) : nullptr;
-    if (job.variant == Variant::Dense) {
+    job.dense_cluster = job.variant == Variant::Dense && p >= SGD_WIDE_P;
+    if (job.dense_cluster) {
+      job.dense_smem = dense_cluster_smem_bytes(K, p);
+      if (job.dense_smem > dense_smem_budget())
+        throw std::invalid_argument("dense x with p = " + std::to_string(p) + " columns: the row ring of one cluster CTA exceeds its shared memory");
+    } else if (job.variant == Variant::Dense) {
       int in_smem = 0;
       job.dense_smem = dense_smem_bytes(K, p, d.ld, &in_smem);
       if (job.dense_smem > dense_smem_budget())
@@ -575,6 +592,18 @@ struct Engine {
     job.prog_ptr = arena.upload_from(job.mirror, 1);
     CK(cudaStreamCreateWithFlags(&job.st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&job.st_prep, cudaStreamNonBlocking));
+    if (f.st != nullptr && l2_persist_bytes > 0) {
+      // the packed coefficient records are gathered and scattered once per nonzero per update while 1.2 KB of row
+      // data per update streams through L2: ask L2 to keep the records (ncu: a quarter of their sectors came from HBM)
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = f.st;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(size_t(p) * sizeof(FeatState), l2_window_max);
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      (void)cudaStreamSetAttribute(job.st, cudaStreamAttributeAccessPolicyWindow, &av);   // a hint: failure is not an error
+      (void)cudaGetLastError();
+    }
     for (cudaEvent_t* ev : {&job.ev0, &job.ev1, &job.ev_f0, &job.ev_f1}) CK(cudaEventCreate(ev));
     for (cudaEvent_t* ev : {&job.ev_idx, &job.ev_prep}) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
@@ -743,7 +772,9 @@ struct Engine {
     // most 32 queues), which caps how many fits of a batch run at once. Batches use the kernels' own %globaltimer
     // brackets (Progress::solver_ns).
     if (use_events()) CK(cudaEventRecord(j.ev0, j.st));
-    if (j.variant == Variant::Dense)
+    if (j.dense_cluster)
+      CK(launch_saga_dense_cluster(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
+    else if (j.variant == Variant::Dense)
       CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else
       CK(launch_saga_sparse(j.variant == Variant::SparseK1, j.dev_ptr, j.prog_ptr, ra, j.st));

@@ -54,6 +54,26 @@ def test_dense_mgaussian_student(cuda, oracle, alpha, standardize_response):
     assert_fit_parity(g.raw, r.raw)
 
 
+@pytest.mark.parametrize("family,K,alpha", [("multinomial", 4, 0.8), ("mgaussian", 3, 1.0), ("binomial", 1, 0.5), ("gaussian", 1, 0.0),
+                                            ("multinomial", 10, 0.0)])
+def test_dense_wide_designs_on_the_cluster_kernel(cuda, oracle, family, K, alpha):
+    """p >= 512: the thread-block-cluster kernel (saga_dense_cluster.cu) and the eight-block dot product of the
+    arithmetic specification; p not a multiple of 256 or 2048, more than one slice per CTA for p = 2500."""
+    rng = np.random.default_rng(17)
+    for n, p in ((300, 530), (200, 2500)):
+        x = rng.normal(size=(n, p)) * (rng.uniform(size=(n, p)) < 0.3)
+        if family == "multinomial":
+            y = np.argmax(x[:, :K] + rng.gumbel(size=(n, K)), axis=1)
+        elif family == "mgaussian":
+            y = x[:, :5] @ rng.normal(size=(5, K)) + 0.5 * rng.normal(size=(n, K))
+        elif family == "binomial":
+            y = (x[:, 0] - x[:, 1] + rng.normal(size=n) > 0).astype(float)
+        else:
+            y = x[:, :4] @ np.array([1.0, -2.0, 0.5, 3.0]) + rng.normal(size=n)
+        g, r = both(cuda, oracle, x, y, family=family, alpha=alpha, nlambda=5, thresh=1e-3, maxit=25, seed=21)
+        assert_fit_parity(g.raw, r.raw)
+
+
 def _heart():
     d = golden("heart")
     n, p = (int(v) for v in d["x_shape"])
