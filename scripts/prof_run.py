@@ -14,7 +14,7 @@ import sgdnet_b200 as sg
 
 what = sys.argv[1] if len(sys.argv) > 1 else "sparse"
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-lib = sg.product()
+lib = sg.product() if not os.environ.get("SGDNET_VARIANT") else _abi.Library(os.path.join(ROOT, "sgdnet_b200", "libsgdnet_b200_" + os.environ["SGDNET_VARIANT"] + ".so"), "sgdnet_")
 ms = C.c_float(0)
 sess = C.c_void_p()
 if what == "sparse":

@@ -155,7 +155,7 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
   return acc;
 }
 
-__global__ void __launch_bounds__(kPassThreads, 3)
+__global__ void __launch_bounds__(kPassThreads)
 loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode, int mask_words) {
   __shared__ double wc_s[32];
   __shared__ double red_s[kPassThreads / 32];

@@ -25,7 +25,8 @@ namespace sgd {
 
 namespace {
 
-constexpr int kCT = 256;        // threads per CTA
+constexpr int kCT = 256;        // feature lanes per CTA (warps 1..8); warp 0 is the control warp
+constexpr int kCBlock = kCT + 32;
 constexpr int kCluster = 8;     // CTAs per fit
 constexpr int kLanes = kCT * kCluster;
 constexpr int kCRing = 4;       // row ring depth
@@ -77,7 +78,7 @@ struct ClusterSmem {
   double* gch;       // [32]
   double* conv;      // [2][kCluster][2]: epoch-end maxima from every CTA
   uint64_t* full;    // [kCRing]
-  uint64_t* pbar;    // [2] partial sums arrived (count kCluster * K)
+  uint64_t* pbar;    // [2] partial sums arrived (count kCluster: one arrival per source CTA)
   uint64_t* cbar;    // [2] epoch-end maxima arrived (count kCluster)
 };
 
@@ -119,7 +120,7 @@ size_t dense_cluster_smem_bytes(int K, int p) {
 
 // KT: class-count bucket (1, 4, 8, 16, 32); PEN: penalty functor. Both compile-time so that the per-class loops unroll.
 template <int KT, int PEN>
-__global__ void __launch_bounds__(kCT, 1)
+__global__ void __launch_bounds__(kCBlock, 1)
 saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool kScalar = (KT == 1);
@@ -136,7 +137,13 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   const bool free_run = (ra.flags & 1) != 0;
   const uint64_t t_start = globaltimer_ns();
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp 0: control warp (exchange, gradient step, row copies); warps 1..8: the CTA's 256 feature lanes. The control
+  // warp owns no features, so the feature warps can prepare the update's step constants (three FP64 divisions) while
+  // the control warp is in the exchange, and nothing but the K-value chain sits between the two block barriers.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool control = warp == 0;
+  const int tid = static_cast<int>(threadIdx.x) - 32;      // feature lane of this CTA (negative in the control warp)
+  const int fwarp = warp - 1;
   const int K = kScalar ? 1 : f.K, p = f.p, ld = f.ld, Ky = f.Ky;
   const int64_t n = f.n;
   const double nd = static_cast<double>(static_cast<uint32_t>(n));
@@ -162,15 +169,15 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   double* Wg = f.W;
   double* Gg = f.gsum;
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int i = 0; i < kCRing; ++i) mbar_init(&sm.full[i], 1);
-    mbar_init(&sm.pbar[0], kCluster * K);
-    mbar_init(&sm.pbar[1], kCluster * K);
+    mbar_init(&sm.pbar[0], kCluster);
+    mbar_init(&sm.pbar[1], kCluster);
     mbar_init(&sm.cbar[0], kCluster);
     mbar_init(&sm.cbar[1], kCluster);
     fence_barrier_init();
   }
-  if (state_in_smem) {
+  if (state_in_smem && !control) {
     for (int i = 0; i < nch; ++i) {
       const int j = feature_of(i);
       for (int k = 0; k < K; ++k) {
@@ -192,9 +199,9 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   };
   uint32_t row_bytes = 0;
   for (int i = 0; i < nch; ++i) row_bytes += slice_bytes(i);
-  auto issue_row = [&](int64_t q) {      // thread 0
+  auto issue_row = [&](int64_t q, uint32_t sq) {      // one thread; sq = seq[q]
     const int slot = static_cast<int>(q % kCRing);
-    const double* src = f.xd + size_t(seq[q]) * ld;
+    const double* src = f.xd + size_t(sq) * ld;
     if (row_bytes == 0) {
       mbar_arrive(&sm.full[slot]);
       return;
@@ -205,12 +212,18 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       if (b) bulk_g2s(sm.ring + (size_t(slot) * nch + i) * kCT, src + kLanes * i + kCT * cta, b, &sm.full[slot]);
     }
   };
+  // row copies are issued by lane 31 of the control warp (not a class lane), one row per update, with the sample index
+  // fetched one update ahead
+  const bool issuer = control && lane == 31;
   int64_t issued = 0;
-  if (tid == 0)
-    for (; issued < kCRing - 1 && issued < total; ++issued) issue_row(issued);
+  uint32_t s_refill = 0;
+  if (issuer) {
+    for (; issued < kCRing - 1 && issued < total; ++issued) issue_row(issued, seq[issued]);
+    if (issued < total) s_refill = seq[issued];
+  }
 
-  // intercept state: class k in lane k of warp 0 of EVERY CTA (identical, redundant)
-  const bool owner = warp == 0 && lane < K;
+  // intercept state: class k in lane k of the control warp of EVERY CTA (identical, redundant)
+  const bool owner = control && lane < K;
   double b_reg = 0.0, gsi_reg = 0.0;
   if (owner) {
     b_reg = f.b[lane];
@@ -250,16 +263,20 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       const double gm_val = (s == prev_s) ? prev_g : ((s == prev2_s) ? prev2_g : gm_cur);
       s_cur = s_nxt;
       if (tg + 2 < total) s_nxt = seq[tg + 2];
+#ifndef SGD_CL_STUDY_NO_SAMPLE_FETCH
       if (owner && tg + 1 < total) {
         y_cur = fetch_y(s_cur);
         gm_cur = fetch_gm(s_cur);
       }
+#endif
 
-      mbar_wait(&sm.full[slot], parity);
       const double* __restrict__ xr = sm.ring + size_t(slot) * nch * kCT;
 
       // ---- A: partial dot products of this lane (ascending j), warp butterfly, warp sums
-      {
+      if (!control) {
+#ifndef SGD_CL_STUDY_NO_ROW_WAIT
+        mbar_wait(&sm.full[slot], parity);
+#endif
         double acc[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) acc[k] = 0.0;
@@ -282,29 +299,45 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < KT; ++k)
-            if (kScalar || k < K) sm.red[warp * 32 + k] = acc[k];
+            if (kScalar || k < K) sm.red[fwarp * 32 + k] = acc[k];
         }
       }
       __syncthreads();   // (1) warp sums visible; every thread is past step C of the previous update
 
-      if (tid == 0 && issued < total) {      // refill the slot the previous update released
-        issue_row(issued);
-        ++issued;
+      // this update's step constants (functions of the deterministic wscale track), in the feature warps while the
+      // control warp exchanges: gamma / wscale, (beta gamma) / wscale with wscale as it will be after this step
+      double gw = 0.0, step = 0.0, thr = 0.0, ws_c = 0.0;
+      const double bgs = beta * gamma * 1.0;
+      if (!control) {
+        ws_c = ((wscale < kSmall) ? 1.0 : wscale) * r;
+        gw = gamma / ws_c;
+        step = gamma / ws_c * 1.0;
+        thr = bgs / ws_c;
       }
 
-      // ---- B: CTA sum (8 warps ascending) -> every CTA; then the 8 CTA sums ascending; gradient (warp 0, redundant)
-      if (warp == 0) {
+      if (issuer && issued < total) {      // refill the slot the previous update released
+        issue_row(issued, s_refill);
+        ++issued;
+        if (issued < total) s_refill = seq[issued];
+      }
+
+      // ---- B: CTA sum (8 warps ascending) -> every CTA; then the 8 CTA sums ascending; gradient (redundant per CTA)
+      if (control) {
         if (lane < K) {
           double tsum = 0.0;
           for (int w = 0; w < 8; ++w) tsum += sm.red[w * 32 + lane];
           const uint32_t my_slot = a_part + ((xpar * kCluster + cta) * 32u + static_cast<uint32_t>(lane)) * 8u;
 #pragma unroll
-          for (uint32_t c = 0; c < kCluster; ++c) {
-            st_cluster_f64(map_to_cta(my_slot, c), tsum);
-            arrive_cluster(map_to_cta(a_pbar + xpar * 8u, c));
-          }
+          for (uint32_t c = 0; c < kCluster; ++c) st_cluster_f64(map_to_cta(my_slot, c), tsum);
         }
+        // ONE arrival per (source CTA, target CTA): lane c arrives on CTA c's barrier once the K lanes' stores are
+        // ordered before it (__syncwarp; the arrive's release is cumulative). Arrivals are serialised at the target
+        // barrier at roughly 125 cycles each: with one per lane and target (8 K per update) they were most of an update.
+        __syncwarp();
+#ifndef SGD_CL_STUDY_NO_EXCHANGE
+        if (lane < kCluster) arrive_cluster(map_to_cta(a_pbar + xpar * 8u, static_cast<uint32_t>(lane)));
         wait_cluster(&sm.pbar[xpar], xphase);
+#endif
         const bool valid = lane < K;
         double lp = 0.0;
         if (valid) {
@@ -341,7 +374,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         prev_g = g;
       }
       if (wscale < kSmall) {
-        for (int i = 0; i < nch; ++i) {
+        for (int i = 0; i < nch && !control; ++i) {
           const int j = feature_of(i);
           if (j < p)
             for (int k = 0; k < K; ++k) {
@@ -356,14 +389,10 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
 
       // ---- C: fused coefficient step, prox, gradient-average update on the owned features
       // (src/saga-dense.h:176-183; penalty functors src/penalties.h:27-79 with scaling = 1)
-      const double gw = gamma / wscale;
-      const double step = gamma / wscale * 1.0;
-      const double bgs = beta * gamma * 1.0;
-      const double thr = bgs / wscale;
       double gch[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) gch[k] = (kScalar || k < K) ? sm.gch[k] : 0.0;
-      for (int i = 0; i < nch; ++i) {
+      for (int i = 0; i < nch && !control; ++i) {
         const int j = feature_of(i);
         if (j >= p) continue;
         const double xj = xr[i * kCT + tid];
@@ -384,7 +413,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         }
         if (PEN == kGroupLasso) {
           const double factor = bgs / sqrt(sq);
-          const double mult = 1.0 - factor / wscale;
+          const double mult = 1.0 - factor / ws_c;
 #pragma unroll
           for (int k = 0; k < KT; ++k)
             if (kScalar || k < K) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
@@ -400,7 +429,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
 
     // ---- epoch end: unscale, convergence over the whole cluster (src/saga-dense.h:188-208, src/utils.h:240-262)
     double mc = 0.0, ms = 0.0;
-    for (int i = 0; i < nch; ++i) {
+    for (int i = 0; i < nch && !control; ++i) {
       const int j = feature_of(i);
       if (j >= p) continue;
       for (int k = 0; k < K; ++k) {
@@ -417,13 +446,13 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
     mc = warp_max(mc);
     ms = warp_max(ms);
     __syncthreads();       // red[] is free again
-    if (lane == 0) {
-      sm.red[warp * 32] = mc;
-      sm.red[warp * 32 + 1] = ms;
+    if (lane == 0 && !control) {
+      sm.red[fwarp * 32] = mc;
+      sm.red[fwarp * 32 + 1] = ms;
     }
     __syncthreads();
     const uint32_t epar = static_cast<uint32_t>(ep & 1), ephase = static_cast<uint32_t>((ep >> 1) & 1);
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       double mc_c = 0.0, ms_c = 0.0;
       for (int w = 0; w < 8; ++w) {
         mc_c = fmax(mc_c, sm.red[w * 32]);
@@ -451,12 +480,12 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   }
 
   // drain copies that were issued but never consumed (early stop) before the shared memory goes away
-  if (tid == 0)
+  if (issuer)
     for (int64_t q = tg; q < issued; ++q)
       mbar_wait(&sm.full[static_cast<int>(q % kCRing)], static_cast<uint32_t>((q / kCRing) & 1));
   __syncthreads();
 
-  if (state_in_smem) {
+  if (state_in_smem && !control) {
     for (int i = 0; i < nch; ++i) {
       const int j = feature_of(i);
       if (j >= p) continue;
@@ -471,7 +500,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
     f.gsi[lane] = gsi_reg;
   }
   cluster_sync_all();      // nobody leaves while another CTA may still write into its shared memory
-  if (cta == 0 && tid == 0) {
+  if (cta == 0 && threadIdx.x == 0) {
     pg.it_outer = it_outer;
     pg.epochs_last_launch = epochs_done;
     if (finished) {
@@ -492,7 +521,7 @@ static cudaError_t launch_cluster_variant(size_t smem, FitDev* fit, Progress* pr
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kCluster, 1, 1);
-  cfg.blockDim = dim3(kCT, 1, 1);
+  cfg.blockDim = dim3(kCBlock, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
