@@ -44,6 +44,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
 __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+// remote store that completes bytes on a (remote) mbarrier: data and signal travel together, no fence on either side
+// (an mbarrier.arrive.release.cluster compiles to MEMBAR.ALL.GPU and its acquire side to an L1 invalidation, CCTL.IVALL -
+// together 45 % of the control warp's time when the exchange used them)
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t mbar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(addr), "d"(v), "r"(mbar_addr)
+               : "memory");
+}
 __device__ __forceinline__ void arrive_cluster(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
@@ -73,17 +80,17 @@ struct ClusterSmem {
   double* ring;      // [kCRing][nch][kCT]
   double* W;         // [K][nch * kCT] (or null: state stays in HBM / L2)
   double* G;
-  double* part;      // [2][kCluster][32]: CTA sums of both parities from every CTA
+  double* part;      // [2][kCluster + 1][32]: CTA sums of both parities from every CTA; row kCluster: gradient memory from CTA 0
   double* red;       // [8 warps][32]
   double* gch;       // [32]
   double* conv;      // [2][kCluster][2]: epoch-end maxima from every CTA
   uint64_t* full;    // [kCRing]
-  uint64_t* pbar;    // [2] partial sums arrived (count kCluster: one arrival per source CTA)
+  uint64_t* pbar;    // [2] partial sums arrived (count 1 + transaction bytes: (kCluster + 1) * K doubles per update)
   uint64_t* cbar;    // [2] epoch-end maxima arrived (count kCluster)
 };
 
 __host__ __device__ inline size_t cluster_fixed_bytes(int nch) {
-  return sizeof(double) * (size_t(kCRing) * nch * kCT + 2 * kCluster * 32 + 8 * 32 + 32 + 2 * kCluster * 2) +
+  return sizeof(double) * (size_t(kCRing) * nch * kCT + 2 * (kCluster + 1) * 32 + 8 * 32 + 32 + 2 * kCluster * 2) +
          sizeof(uint64_t) * (kCRing + 4);
 }
 
@@ -91,7 +98,7 @@ __device__ __forceinline__ ClusterSmem carve_cluster(unsigned char* base, int K,
   ClusterSmem s;
   size_t off = 0;
   s.ring = reinterpret_cast<double*>(base + off); off += sizeof(double) * size_t(kCRing) * nch * kCT;
-  s.part = reinterpret_cast<double*>(base + off); off += sizeof(double) * 2 * kCluster * 32;
+  s.part = reinterpret_cast<double*>(base + off); off += sizeof(double) * 2 * (kCluster + 1) * 32;
   s.red = reinterpret_cast<double*>(base + off); off += sizeof(double) * 8 * 32;
   s.gch = reinterpret_cast<double*>(base + off); off += sizeof(double) * 32;
   s.conv = reinterpret_cast<double*>(base + off); off += sizeof(double) * 2 * kCluster * 2;
@@ -171,8 +178,8 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCRing; ++i) mbar_init(&sm.full[i], 1);
-    mbar_init(&sm.pbar[0], kCluster);
-    mbar_init(&sm.pbar[1], kCluster);
+    mbar_init(&sm.pbar[0], 1);
+    mbar_init(&sm.pbar[1], 1);
     mbar_init(&sm.cbar[0], kCluster);
     mbar_init(&sm.cbar[1], kCluster);
     fence_barrier_init();
@@ -238,11 +245,11 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   double prev_g = 0.0, prev2_g = 0.0;
   bool finished = false;
 
-  // per-sample operands one update ahead; the gradient memory of the last two samples is forwarded from registers.
-  // CTA 0 stores the gradient memory, the others read it with .cg (another SM's L1 may hold the line from an earlier
-  // draw of the same sample in this launch)
+  // per-sample operands one update ahead. The gradient memory is read and written by CTA 0 ALONE (same lanes, so program
+  // order is all the coherence it needs; the last two samples are forwarded from registers because their stores may
+  // still be in flight when the next value is prefetched) and travels to the other CTAs with CTA 0's partial sums.
   auto fetch_y = [&](uint32_t sx) { return f.yt[size_t(sx) * Ky + (Ky == 1 ? 0 : lane)]; };
-  auto fetch_gm = [&](uint32_t sx) { return ldcg_f64(f.gmem + size_t(sx) * K + lane); };
+  auto fetch_gm = [&](uint32_t sx) { return cta == 0 ? f.gmem[size_t(sx) * K + lane] : 0.0; };
   uint32_t s_cur = seq[0], s_nxt = (total > 1) ? seq[1] : 0u;
   double y_cur = 0.0, gm_cur = 0.0;
   if (owner) {
@@ -260,7 +267,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       const uint32_t xpar = static_cast<uint32_t>(tg & 1);                // exchange buffer of this update
       const uint32_t xphase = static_cast<uint32_t>((tg >> 1) & 1);       // phase of pbar[xpar]
       const double y_val = y_cur;
-      const double gm_val = (s == prev_s) ? prev_g : ((s == prev2_s) ? prev2_g : gm_cur);
+      const double gm_mine = (s == prev_s) ? prev_g : ((s == prev2_s) ? prev2_g : gm_cur);     // meaningful in CTA 0
       s_cur = s_nxt;
       if (tg + 2 < total) s_nxt = seq[tg + 2];
 #ifndef SGD_CL_STUDY_NO_SAMPLE_FETCH
@@ -326,23 +333,24 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         if (lane < K) {
           double tsum = 0.0;
           for (int w = 0; w < 8; ++w) tsum += sm.red[w * 32 + lane];
-          const uint32_t my_slot = a_part + ((xpar * kCluster + cta) * 32u + static_cast<uint32_t>(lane)) * 8u;
+          const uint32_t my_slot = a_part + ((xpar * (kCluster + 1) + cta) * 32u + static_cast<uint32_t>(lane)) * 8u;
+          const uint32_t gm_slot = a_part + ((xpar * (kCluster + 1) + kCluster) * 32u + static_cast<uint32_t>(lane)) * 8u;
 #pragma unroll
-          for (uint32_t c = 0; c < kCluster; ++c) st_cluster_f64(map_to_cta(my_slot, c), tsum);
+          for (uint32_t c = 0; c < kCluster; ++c) {
+            const uint32_t bar_c = map_to_cta(a_pbar + xpar * 8u, c);
+            st_async_f64(map_to_cta(my_slot, c), tsum, bar_c);
+            if (cta == 0) st_async_f64(map_to_cta(gm_slot, c), gm_mine, bar_c);
+          }
         }
-        // ONE arrival per (source CTA, target CTA): lane c arrives on CTA c's barrier once the K lanes' stores are
-        // ordered before it (__syncwarp; the arrive's release is cumulative). Arrivals are serialised at the target
-        // barrier at roughly 125 cycles each: with one per lane and target (8 K per update) they were most of an update.
-        __syncwarp();
-#ifndef SGD_CL_STUDY_NO_EXCHANGE
-        if (lane < kCluster) arrive_cluster(map_to_cta(a_pbar + xpar * 8u, static_cast<uint32_t>(lane)));
-        wait_cluster(&sm.pbar[xpar], xphase);
-#endif
+        // this CTA expects (kCluster + 1) * K doubles per update on its own barrier: one local arrival arms the phase
+        if (lane == 0) mbar_expect_tx(&sm.pbar[xpar], static_cast<uint32_t>((kCluster + 1) * K * 8));
+        mbar_wait(&sm.pbar[xpar], xphase);
+        const double gm_val = (lane < K) ? sm.part[(xpar * (kCluster + 1) + kCluster) * 32 + lane] : 0.0;
         const bool valid = lane < K;
         double lp = 0.0;
         if (valid) {
           double dot = 0.0;
-          for (int c = 0; c < kCluster; ++c) dot += sm.part[(xpar * kCluster + c) * 32 + lane];
+          for (int c = 0; c < kCluster; ++c) dot += sm.part[(xpar * (kCluster + 1) + c) * 32 + lane];
           lp = dot * wscale + b_reg;
         }
         double g;
