@@ -776,7 +776,7 @@ struct Engine {
     // brackets (Progress::solver_ns).
     if (use_events()) CK(cudaEventRecord(j.ev0, j.st));
     if (j.dense_cluster)
-      CK(launch_saga_dense_cluster(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
+      CK(launch_saga_dense_cluster(j.dev.K, j.dev.p, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else if (j.variant == Variant::Dense)
       CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else

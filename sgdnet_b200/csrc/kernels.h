@@ -26,9 +26,11 @@ size_t dense_smem_bytes(int K, int p, int ld, int* state_in_smem);
 size_t dense_smem_budget();
 cudaError_t launch_saga_dense(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 int dense_kt_bucket(int K);
-// designs with p >= SGD_WIDE_P: one thread-block cluster of 8 CTAs per fit (saga_dense_cluster.cu)
+// 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for
+// designs with p >= SGD_WIDE_P: one thread-block cluster of 8 CTAs per fit (saga_dense_cluster.cu; shapes without a
+// compile-time instantiation there go to saga_dense_cluster_generic.cu)
 size_t dense_cluster_smem_bytes(int K, int p);
-cudaError_t launch_saga_dense_cluster(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);   // 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for
+cudaError_t launch_saga_dense_cluster(int K, int p, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 
 // Conflict codes of a staged sequence for the wavefront kernel (sparse K == 1); a function of the sequence alone, so it

@@ -1,27 +1,38 @@
 // saga_dense_cluster.cu — dense SAGA epochs on a thread-block cluster (reference: src/saga-dense.h:147-212), for
-// designs with p >= kWideP features (BASELINE configs 3 and 4).
+// designs with p >= SGD_WIDE_P features (BASELINE configs 3 and 4).
 //
-// One cluster of 8 CTAs x 256 threads per fit = 2048 lanes. Lane L = 256 * cta + tid owns the features j = L, L + 2048,
-// ... for ALL classes: their W and g_sum live in that CTA's shared memory for the whole launch and are touched by no
-// other thread, so the dense sweeps of the reference's update (the K x p matrix-vector product, the coefficient step,
-// the prox over all p features and the g_sum update, src/saga-dense.h:154, 176-183) are split 2048 ways. What crosses
-// threads per update is only the K partial dot products:
-//   lane: running sum over its features (ascending j)  ->  xor-butterfly inside each warp  ->  the CTA's 8 warp sums
-//   added in ascending order  ->  the 8 CTA sums exchanged all-to-all through DISTRIBUTED SHARED MEMORY (each CTA
-//   stores its K values into the other CTAs' shared memory and arrives on their mbarrier with release.cluster)  ->
-//   every CTA adds the 8 CTA sums in ascending order and runs the (K-value) gradient step redundantly, so no second
-//   exchange is needed; CTA 0 alone stores the gradient memory.
-// That association is the arithmetic specification of a wide dense dot product (include/sgdnet_arith.h, item 2) and is
-// what the oracle's portable mode computes (oracle/sgdnet_oracle.cpp dot_dense_wide).
-// A CTA streams only ITS 256-feature slices of each sampled row: 1-D bulk copies (cp.async.bulk -> UBLKCP) into a
-// shared-memory ring, kRing - 1 rows ahead, driven by the sampling sequence.
+// One cluster of 8 CTAs per fit; a CTA is 8 feature warps (256 lanes) + 1 control warp. Feature lane L = 256 * cta + tid
+// owns the features j = L, L + 2048, ... for ALL classes. Their W and g_sum stay in that lane's REGISTERS for the whole
+// launch when slices x classes <= 16 (configs 3 and 4), otherwise in the CTA's shared memory; nobody else touches
+// them, so the dense sweeps of the reference's update (the K x p matrix-vector product, the coefficient step, the prox
+// over all p features and the g_sum update, src/saga-dense.h:154, 176-183) are split 2048 ways. What crosses threads
+// per update is the K partial dot products, with the association of include/sgdnet_arith.h item 2 (= the oracle's
+// dot_dense_wide):
+//   lane: running sum over its features (ascending j)
+//   warp: the xor-butterfly 16, 8, 4, 2, 1 - computed by recursive halving: at offset o a lane keeps one half of its
+//         class sums and hands the other half to lane ^ o, so a level moves K/2, K/4, ... values instead of K (the
+//         SHFL unit, one warp-instruction per cycle per SM, is what bounded the plain butterfly); each pair sum
+//         a_i + a_(i^o) is formed once, by either partner - same operands, same bits
+//   CTA:  the 8 warp sums added in ascending order by the control warp (class k in lane k)
+//   cluster: the 8 CTA sums exchanged all-to-all through DISTRIBUTED SHARED MEMORY - st.async into the other CTAs'
+//         shared memory, completing bytes on their mbarrier, so data and signal travel together and neither side
+//         fences - and added in ascending order by every control warp, which then runs the K-value gradient step
+//         redundantly: no second exchange. CTA 0 alone reads and writes the gradient memory; its value rides along.
+// Inside a CTA the two hand-overs per update are named barriers used one way (bar.arrive by the producer side,
+// bar.sync by the consumer side): the feature warps never wait for "warp sums taken", the control warp never waits
+// for "g_change taken". Everything that is not on the path warp sums -> g_change (intercept step, gradient-memory
+// store, next sample's operands, the next row's bulk copies, the step constants' three divisions) runs in the
+// slack of the side that is waiting anyway.
+// A CTA streams only ITS 256-feature slices of each sampled row: 1-D bulk copies (cp.async.bulk -> UBLKCP) into an
+// 8-deep shared-memory ring driven by the sampling sequence.
 // Algorithmic HBM bytes per update: 8*p (row) + 4 (index) + 8*K_y (y) + 16*K (gradient memory read + write).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sgd {
+
+size_t dense_cluster_generic_smem_bytes(int K, int p);
+cudaError_t launch_saga_dense_cluster_generic(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 
 namespace {
 
@@ -29,11 +40,17 @@ constexpr int kCT = 256;        // feature lanes per CTA (warps 1..8); warp 0 is
 constexpr int kCBlock = kCT + 32;
 constexpr int kCluster = 8;     // CTAs per fit
 constexpr int kLanes = kCT * kCluster;
-constexpr int kCRing = 4;       // row ring depth
+constexpr int kCRing = 8;       // row ring depth (power of two)
+constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
@@ -41,99 +58,161 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-// remote store that completes bytes on a (remote) mbarrier: data and signal travel together, no fence on either side
-// (an mbarrier.arrive.release.cluster compiles to MEMBAR.ALL.GPU and its acquire side to an L1 invalidation, CCTL.IVALL -
-// together 45 % of the control warp's time when the exchange used them)
+// remote store that completes bytes on a (remote) mbarrier
 __device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t mbar_addr) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(addr), "d"(v), "r"(mbar_addr)
                : "memory");
 }
-__device__ __forceinline__ void arrive_cluster(uint32_t bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
-}
-__device__ __forceinline__ void wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ double ldcg_f64(const double* p) {
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
+// named barriers used one way: producers arrive, consumers sync (both name the full block as the expected count)
+__device__ __forceinline__ void bar_arrive_named(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kCBlock) : "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kCBlock) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-struct ClusterSmem {
-  double* ring;      // [kCRing][nch][kCT]
-  double* W;         // [K][nch * kCT] (or null: state stays in HBM / L2)
-  double* G;
-  double* part;      // [2][kCluster + 1][32]: CTA sums of both parities from every CTA; row kCluster: gradient memory from CTA 0
-  double* red;       // [8 warps][32]
-  double* gch;       // [32]
-  double* conv;      // [2][kCluster][2]: epoch-end maxima from every CTA
-  uint64_t* full;    // [kCRing]
-  uint64_t* pbar;    // [2] partial sums arrived (count 1 + transaction bytes: (kCluster + 1) * K doubles per update)
-  uint64_t* cbar;    // [2] epoch-end maxima arrived (count kCluster)
+#ifdef SGD_CL_TRACE
+// Timeline trace (measurement build only): clock64 of eight events per update for updates [kClFrom, kClFrom + kClRows) of a
+// launch, CTA 0 only.  control warp: 0 warp sums in hand (past barrier 1), 1 exchange stores issued, 2 all CTA sums
+// arrived, 3 g_change stored.  feature warp 0: 5 row in the ring, 6 warp sums stored, 8 g_change in hand (past barrier 2),
+// 9 coefficient step done.
+constexpr int64_t kClFrom = 20000, kClRows = 4096;
+__device__ long long g_cl_trace[kClRows][10];
+__device__ __forceinline__ long long clock_ordered() {      // ordered with the barriers and memory operations around it
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define CLTRACE(ev, cond) do { if ((cond) && cta == 0 && lane == 0 && tg - kClFrom >= 0 && tg - kClFrom < kClRows) g_cl_trace[tg - kClFrom][ev] = clock_ordered(); } while (0)
+#else
+#define CLTRACE(ev, cond)
+#endif
+
+template <int NCH>
+struct __align__(128) ClusterFixed {
+  double ring[kCRing][NCH][kCT];
+  double part[2][kCluster + 1][32];   // CTA sums of both parities from every CTA; row kCluster: gradient memory from CTA 0
+  double red[8][32];                  // warp sums, class-indexed
+  double gch[32];
+  double conv[2][kCluster][2];        // epoch-end maxima from every CTA
+  double cred[8][2];
+  uint64_t full[kCRing];
+  uint64_t pbar[2];                   // partial sums arrived (count 1 + transaction bytes: (kCluster + 1) * K doubles per update)
+  uint64_t cbar[2];                   // epoch-end maxima arrived (count 1 + transaction bytes)
 };
 
-__host__ __device__ inline size_t cluster_fixed_bytes(int nch) {
-  return sizeof(double) * (size_t(kCRing) * nch * kCT + 2 * (kCluster + 1) * 32 + 8 * 32 + 32 + 2 * kCluster * 2) +
-         sizeof(uint64_t) * (kCRing + 4);
+constexpr bool cluster_reg_state(int KT, int NCH) { return KT * NCH <= 16; }
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+
+// Recursive-halving form of the 32-lane xor-butterfly over N class sums per lane (N a power of two <= 32). Returns, in
+// every lane, the butterfly total of class (lane >> (5 - log2 N)).
+template <int N, int O>
+struct Halving {
+  static __device__ __forceinline__ double run(double (&v)[N], int lane) {
+    if constexpr (O == 0) {
+      return v[0];
+    } else if constexpr (N == 1) {
+      double h[1] = {v[0] + __shfl_xor_sync(kFull, v[0], O)};
+      return Halving<1, O / 2>::run(h, lane);
+    } else {
+      const bool up = (lane & O) != 0;
+      double h[N / 2];
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        const double keep = up ? v[N / 2 + i] : v[i];
+        const double send = up ? v[i] : v[N / 2 + i];
+        h[i] = keep + __shfl_xor_sync(kFull, send, O);
+      }
+      return Halving<N / 2, O / 2>::run(h, lane);
+    }
+  }
+};
+
+// sgd_log (include/sgdnet_arith.h) for arguments in [1, 64] - a sum of at most 32 exponentials of non-positive numbers
+// of which one is exp(0): the same operations, hence the same bits, without the special-case exits in front of them;
+// anything else (a NaN from a diverged fit) takes sgd_log itself.
+static __device__ __noinline__ double sgd_log_rare(double x) { return sgd_log(x); }
+__device__ __forceinline__ double sgd_log_sum(double x) {
+  const uint32_t hi = static_cast<uint32_t>(__double2hiint(x)), lo = static_cast<uint32_t>(__double2loint(x));
+  int32_t k = static_cast<int32_t>(hi >> 20) - 1023;
+  const uint32_t mant_hi = hi & 0x000fffffu;
+  // mantissa > 0x6a09e667f3bcc  <=>  m >= sqrt(2): use m/2 and k+1
+  const bool big = mant_hi > 0x6a09eu || (mant_hi == 0x6a09eu && lo > 0x667f3bccu);
+  k += big ? 1 : 0;
+  const double m = __hiloint2double(static_cast<int>(mant_hi | (big ? 0x3fe00000u : 0x3ff00000u)), static_cast<int>(lo));
+  const double f = m - 1.0;
+  const double dk = static_cast<double>(k);
+  const double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 +
+                         w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double out = dk * kLn2Hi - ((hfsq - (s * (hfsq + R) + dk * kLn2Lo)) - f);
+  if (__builtin_expect(!(x >= 1.0 && x <= 64.0), 0)) return sgd_log_rare(x);
+  return out;
 }
 
-__device__ __forceinline__ ClusterSmem carve_cluster(unsigned char* base, int K, int nch, bool state_in_smem) {
-  ClusterSmem s;
-  size_t off = 0;
-  s.ring = reinterpret_cast<double*>(base + off); off += sizeof(double) * size_t(kCRing) * nch * kCT;
-  s.part = reinterpret_cast<double*>(base + off); off += sizeof(double) * 2 * (kCluster + 1) * 32;
-  s.red = reinterpret_cast<double*>(base + off); off += sizeof(double) * 8 * 32;
-  s.gch = reinterpret_cast<double*>(base + off); off += sizeof(double) * 32;
-  s.conv = reinterpret_cast<double*>(base + off); off += sizeof(double) * 2 * kCluster * 2;
-  s.full = reinterpret_cast<uint64_t*>(base + off); off += sizeof(uint64_t) * kCRing;
-  s.pbar = reinterpret_cast<uint64_t*>(base + off); off += sizeof(uint64_t) * 2;
-  s.cbar = reinterpret_cast<uint64_t*>(base + off); off += sizeof(uint64_t) * 2;
-  off = (off + 15) & ~size_t(15);
-  if (state_in_smem) {
-    s.W = reinterpret_cast<double*>(base + off); off += sizeof(double) * size_t(K) * nch * kCT;
-    s.G = reinterpret_cast<double*>(base + off);
-  } else {
-    s.W = nullptr;
-    s.G = nullptr;
-  }
-  return s;
+// LogSumExp (src/math.h:25-33) over the classes held one per lane (lanes that hold no class pass valid = false), the
+// bits of lse_warp (common.cuh), for at most KT classes in lanes 0 .. KT-1. The maximum is exact in any order: two
+// integer warp reductions over an order-preserving key replace five shuffle-and-compare rounds. The sum is the
+// 32-slot butterfly padded with zeros (include/sgdnet_arith.h, item 2): the levels whose partner lanes all hold the
+// pad (offsets >= KT) add +0.0 to a non-negative number and are skipped.
+template <int KT>
+__device__ __forceinline__ double lse_classes(double lp, bool valid, int lane) {
+  const long long b = __double_as_longlong(valid ? lp : -INFINITY);
+  const unsigned long long key = b < 0 ? ~static_cast<unsigned long long>(b) : (static_cast<unsigned long long>(b) | 0x8000000000000000ull);
+  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
+  const unsigned hmax = __reduce_max_sync(kFull, hi);
+  const unsigned lmax = __reduce_max_sync(kFull, hi == hmax ? lo : 0u);
+  const unsigned long long kmax = (static_cast<unsigned long long>(hmax) << 32) | lmax;
+  const double mx = __longlong_as_double((kmax >> 63) ? static_cast<long long>(kmax & 0x7fffffffffffffffull) : static_cast<long long>(~kmax));
+  double e = valid ? sgd_exp_inrange(lp - mx) : 0.0;
+#pragma unroll
+  for (int o = (KT >= 32 ? 16 : KT / 2); o > 0; o >>= 1) e += __shfl_xor_sync(kFull, e, o);
+  const double sum = (lane < KT) ? e : 1.0;      // lanes beyond the first group hold no class and no sum
+  return sgd_log_sum(sum) + mx;
+}
+
+// div_by_n (common.cuh) with the way out deferred: instead of calling the IEEE division for an operand outside the safe
+// exponent range, it raises `rare`, and the caller redoes its quotients with the division once, after the straight-line
+// code. Keeps a sweep over several classes free of branches, so the classes' dependent chains overlap.
+__device__ __forceinline__ double div_by_n_flag(double a, double nd, double rn, bool& rare) {
+  const uint32_t hi = static_cast<uint32_t>(__double2hiint(a));
+  const uint32_t ex = (hi >> 20) & 0x7ffu;
+  const bool ok = (ex - 127u) <= 1792u;
+  const double q0 = a * rn;
+  const double r0 = fma(-q0, nd, a);
+  const double q1 = fma(r0, rn, q0);
+  const bool zero = ((hi << 1) | static_cast<uint32_t>(__double2loint(a))) == 0u;
+  rare |= !ok && !zero;
+  return ok ? q1 : a;       // a == +-0 when !ok && zero
 }
 
 }  // namespace
 
-size_t dense_cluster_smem_bytes(int K, int p) {
-  const int nch = (p + kLanes - 1) / kLanes;
-  const size_t fixed = (cluster_fixed_bytes(nch) + 15) & ~size_t(15);
-  const size_t state = sizeof(double) * 2 * size_t(K) * nch * kCT;
-  return (fixed + state <= dense_smem_budget()) ? fixed + state : fixed;
-}
+#ifdef SGD_CL_TRACE
+}  // namespace sgd
+extern "C" void sgdnet_debug_cluster_trace(long long* out) { cudaMemcpyFromSymbol(out, sgd::g_cl_trace, sizeof(sgd::g_cl_trace)); }
+namespace sgd {
+#endif
 
-// KT: class-count bucket (1, 4, 8, 16, 32); PEN: penalty functor. Both compile-time so that the per-class loops unroll.
-template <int KT, int PEN>
+namespace {
+
+// KT: class-count bucket (1, 4, 8, 16, 32); PEN: penalty functor; NCH: 256-feature slices per CTA and row (1, 2, 4).
+template <int KT, int PEN, int NCH>
 __global__ void __launch_bounds__(kCBlock, 1)
 saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr bool kScalar = (KT == 1);
+  constexpr bool kReg = cluster_reg_state(KT, NCH);
+  constexpr int kNF = NCH * kCT;
   Progress& pg = *prog;
   const FitDev& f = *fit;
   const uint32_t cta = cluster_ctarank();
+  const uint32_t nct = cluster_nctarank();     // 2, 4 or 8 CTAs: as many 256-feature blocks as the design has (at most 8)
   if (ra.n_epochs <= 0 || pg.status != kRunning) {       // uniform over the cluster
     if (cta == 0 && threadIdx.x == 0) {
       pg.epochs_last_launch = 0;
@@ -144,342 +223,349 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   const bool free_run = (ra.flags & 1) != 0;
   const uint64_t t_start = globaltimer_ns();
 
-  // warp 0: control warp (exchange, gradient step, row copies); warps 1..8: the CTA's 256 feature lanes. The control
-  // warp owns no features, so the feature warps can prepare the update's step constants (three FP64 divisions) while
-  // the control warp is in the exchange, and nothing but the K-value chain sits between the two block barriers.
+  ClusterFixed<NCH>& sm = *reinterpret_cast<ClusterFixed<NCH>*>(smem_raw);
+  double* const Ws = reinterpret_cast<double*>(smem_raw + sizeof(ClusterFixed<NCH>));   // [KT][NCH * 256] when !kReg
+  double* const Gs = Ws + (kReg ? 0 : KT * kNF);
+
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool control = warp == 0;
   const int tid = static_cast<int>(threadIdx.x) - 32;      // feature lane of this CTA (negative in the control warp)
   const int fwarp = warp - 1;
-  const int K = kScalar ? 1 : f.K, p = f.p, ld = f.ld, Ky = f.Ky;
+  const int K = f.K, p = f.p, ld = f.ld, Ky = f.Ky;
   const int64_t n = f.n;
   const double nd = static_cast<double>(static_cast<uint32_t>(n));
   const double rn = 1.0 / nd;
   const int family = f.family;
   const bool fit_intercept = f.fit_intercept != 0;
-  const int nch = (p + kLanes - 1) / kLanes;             // 256-feature slices per CTA and row
-  const int nf = nch * kCT;                               // feature slots of this CTA (some beyond p)
-
-  uint32_t dyn_bytes;
-  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
-  const size_t fixed = (cluster_fixed_bytes(nch) + 15) & ~size_t(15);
-  const bool state_in_smem = fixed + sizeof(double) * 2 * size_t(K) * nf <= size_t(dyn_bytes);
-  ClusterSmem sm = carve_cluster(smem_raw, K, nch, state_in_smem);
 
   const int li = pg.lambda_ind;
   const double gamma = f.gamma[li], alpha = f.alpha[li], beta = f.beta[li];
   const double r = 1.0 - alpha * gamma;     // wscale_update
+  const double bgs = beta * gamma * 1.0;
 
-  // feature slot q = i * 256 + tid  <->  feature j = 2048 * i + 256 * cta + tid
-  auto feature_of = [&](int i) { return kLanes * i + kCT * static_cast<int>(cta) + tid; };
-  // state addressing: shared memory [k][slot] or global class-major [k][j]
-  double* Wg = f.W;
-  double* Gg = f.gsum;
+  double* const Wg = f.W;
+  double* const Gg = f.gsum;
+  const uint32_t* __restrict__ seq = ra.seq;
+  const int64_t total = n * ra.n_epochs;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCRing; ++i) mbar_init(&sm.full[i], 1);
     mbar_init(&sm.pbar[0], 1);
     mbar_init(&sm.pbar[1], 1);
-    mbar_init(&sm.cbar[0], kCluster);
-    mbar_init(&sm.cbar[1], kCluster);
+    mbar_init(&sm.cbar[0], 1);
+    mbar_init(&sm.cbar[1], 1);
     fence_barrier_init();
   }
-  if (state_in_smem && !control) {
-    for (int i = 0; i < nch; ++i) {
-      const int j = feature_of(i);
-      for (int k = 0; k < K; ++k) {
-        sm.W[size_t(k) * nf + i * kCT + tid] = j < p ? Wg[size_t(k) * p + j] : 0.0;
-        sm.G[size_t(k) * nf + i * kCT + tid] = j < p ? Gg[size_t(k) * p + j] : 0.0;
+  for (int i = threadIdx.x; i < 2 * (kCluster + 1) * 32; i += kCBlock) (&sm.part[0][0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < 8 * 32; i += kCBlock) (&sm.red[0][0])[i] = 0.0;
+
+  // feature slot (i, tid)  <->  feature j = 2048 * i + 256 * cta + tid
+  const int jbase = kCT * static_cast<int>(cta) + tid;
+  double Wr[kReg ? NCH * KT : 1], Gr[kReg ? NCH * KT : 1];
+  if (!control) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int j = kLanes * i + jbase;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const bool have = j < p && k < K;
+        const double w0 = have ? Wg[size_t(k) * p + j] : 0.0;
+        const double g0 = have ? Gg[size_t(k) * p + j] : 0.0;
+        if constexpr (kReg) {
+          Wr[i * KT + k] = w0;
+          Gr[i * KT + k] = g0;
+        } else {
+          Ws[(k * NCH + i) * kCT + tid] = w0;
+          Gs[(k * NCH + i) * kCT + tid] = g0;
+        }
       }
     }
   }
   __syncthreads();
   cluster_sync_all();       // every CTA's barriers exist before anybody arrives on them remotely
 
+  double wscale = 1.0;
+  uint32_t it_outer = pg.it_outer;
+  uint32_t epochs_done = 0;
+  int64_t tg = 0;
+  bool finished = false;
+
+  // ------------------------------------------------------------------ control warp state
   // this CTA's slices of a row: slice i covers features [2048 i + 256 cta, +256) clipped to the row's padded length
-  const uint32_t* __restrict__ seq = ra.seq;
-  const int64_t total = n * ra.n_epochs;
-  auto slice_bytes = [&](int i) {
+  uint32_t slice_b[NCH];
+  uint32_t row_bytes = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
     const int j0 = kLanes * i + kCT * static_cast<int>(cta);
     const int len = (j0 >= ld) ? 0 : ((ld - j0 < kCT) ? ld - j0 : kCT);
-    return static_cast<uint32_t>(len) * 8u;
-  };
-  uint32_t row_bytes = 0;
-  for (int i = 0; i < nch; ++i) row_bytes += slice_bytes(i);
+    slice_b[i] = static_cast<uint32_t>(len) * 8u;
+    row_bytes += slice_b[i];
+  }
   auto issue_row = [&](int64_t q, uint32_t sq) {      // one thread; sq = seq[q]
-    const int slot = static_cast<int>(q % kCRing);
-    const double* src = f.xd + size_t(sq) * ld;
+    const int slot = static_cast<int>(q & (kCRing - 1));
+    const double* src = f.xd + size_t(sq) * ld + kCT * cta;
     if (row_bytes == 0) {
       mbar_arrive(&sm.full[slot]);
       return;
     }
     mbar_expect_tx(&sm.full[slot], row_bytes);
-    for (int i = 0; i < nch; ++i) {
-      const uint32_t b = slice_bytes(i);
-      if (b) bulk_g2s(sm.ring + (size_t(slot) * nch + i) * kCT, src + kLanes * i + kCT * cta, b, &sm.full[slot]);
-    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      if (slice_b[i]) bulk_g2s(&sm.ring[slot][i][0], src + kLanes * i, slice_b[i], &sm.full[slot]);
   };
-  // row copies are issued by lane 31 of the control warp (not a class lane), one row per update, with the sample index
-  // fetched one update ahead
   const bool issuer = control && lane == 31;
-  int64_t issued = 0;
   uint32_t s_refill = 0;
   if (issuer) {
-    for (; issued < kCRing - 1 && issued < total; ++issued) issue_row(issued, seq[issued]);
-    if (issued < total) s_refill = seq[issued];
+    for (int64_t q = 0; q < kCRing && q < total; ++q) issue_row(q, seq[q]);
+    if (kCRing < total) s_refill = seq[kCRing];
   }
-
   // intercept state: class k in lane k of the control warp of EVERY CTA (identical, redundant)
-  const bool owner = control && lane < K;
+  const bool valid = control && lane < K;
   double b_reg = 0.0, gsi_reg = 0.0;
-  if (owner) {
-    b_reg = f.b[lane];
-    gsi_reg = f.gsi[lane];
-  }
-
-  double wscale = 1.0;
-  uint32_t it_outer = pg.it_outer;
-  uint32_t epochs_done = 0;
-  int64_t tg = 0;
-  uint32_t prev_s = 0xffffffffu, prev2_s = 0xffffffffu;
-  double prev_g = 0.0, prev2_g = 0.0;
-  bool finished = false;
-
-  // per-sample operands one update ahead. The gradient memory is read and written by CTA 0 ALONE (same lanes, so program
-  // order is all the coherence it needs; the last two samples are forwarded from registers because their stores may
-  // still be in flight when the next value is prefetched) and travels to the other CTAs with CTA 0's partial sums.
+  // per-sample operands one update ahead. The gradient memory is read and written by CTA 0 ALONE, by the same lanes and
+  // with the store of update t ahead of the load for update t + 1 in program order, which is all the coherence it needs;
+  // it travels to the other CTAs with CTA 0's partial sums.
   auto fetch_y = [&](uint32_t sx) { return f.yt[size_t(sx) * Ky + (Ky == 1 ? 0 : lane)]; };
-  auto fetch_gm = [&](uint32_t sx) { return cta == 0 ? f.gmem[size_t(sx) * K + lane] : 0.0; };
-  uint32_t s_cur = seq[0], s_nxt = (total > 1) ? seq[1] : 0u;
+  uint32_t s_cur = 0, s_n1 = 0, s_n2 = 0;
   double y_cur = 0.0, gm_cur = 0.0;
-  if (owner) {
-    y_cur = fetch_y(s_cur);
-    gm_cur = fetch_gm(s_cur);
+  uint32_t a_mine = 0, a_pbar = 0;      // this lane's slot in part[0][cta][] and pbar[0], as shared-window addresses
+  if (control) {
+    s_cur = seq[0];
+    s_n1 = (total > 1) ? seq[1] : 0u;
+    s_n2 = (total > 2) ? seq[2] : 0u;
+    if (valid) {
+      b_reg = f.b[lane];
+      gsi_reg = f.gsi[lane];
+      y_cur = fetch_y(s_cur);
+      if (cta == 0) gm_cur = f.gmem[size_t(s_cur) * K + lane];
+    }
+    a_mine = smem_u32(&sm.part[0][cta][lane]);
+    a_pbar = smem_u32(&sm.pbar[0]);
   }
-
-  const uint32_t a_part = smem_u32(sm.part), a_pbar = smem_u32(sm.pbar);
+  constexpr uint32_t kParStride = (kCluster + 1) * 32 * 8;                 // bytes between the two parities of part[]
+  constexpr uint32_t kGmOffset = (kCluster * 32) * 8;                      // part[.][kCluster][lane] - part[.][0][lane]
 
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep) {
-    for (int64_t t = 0; t < n; ++t, ++tg) {
-      const uint32_t s = s_cur;
-      const int slot = static_cast<int>(tg % kCRing);
-      const uint32_t parity = static_cast<uint32_t>((tg / kCRing) & 1);
-      const uint32_t xpar = static_cast<uint32_t>(tg & 1);                // exchange buffer of this update
-      const uint32_t xphase = static_cast<uint32_t>((tg >> 1) & 1);       // phase of pbar[xpar]
-      const double y_val = y_cur;
-      const double gm_mine = (s == prev_s) ? prev_g : ((s == prev2_s) ? prev2_g : gm_cur);     // meaningful in CTA 0
-      s_cur = s_nxt;
-      if (tg + 2 < total) s_nxt = seq[tg + 2];
-#ifndef SGD_CL_STUDY_NO_SAMPLE_FETCH
-      if (owner && tg + 1 < total) {
-        y_cur = fetch_y(s_cur);
-        gm_cur = fetch_gm(s_cur);
-      }
-#endif
-
-      const double* __restrict__ xr = sm.ring + size_t(slot) * nch * kCT;
-
-      // ---- A: partial dot products of this lane (ascending j), warp butterfly, warp sums
-      if (!control) {
-#ifndef SGD_CL_STUDY_NO_ROW_WAIT
-        mbar_wait(&sm.full[slot], parity);
-#endif
-        double acc[KT];
+    if (control) {
+      // ================================================================ control warp
+      for (int64_t t = 0; t < n; ++t, ++tg) {
+        const uint32_t xpar = static_cast<uint32_t>(tg & 1);                // exchange buffer of this update
+        const uint32_t xphase = static_cast<uint32_t>((tg >> 1) & 1);       // phase of pbar[xpar]
+        bar_sync_named(1);                                                  // warp sums are in red[]
+        CLTRACE(0, true);
+        double tsum = 0.0;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] = 0.0;
-        for (int i = 0; i < nch; ++i) {
-          const int j = feature_of(i);
-          if (j < p) {
-            const double xj = xr[i * kCT + tid];
-#pragma unroll
-            for (int k = 0; k < KT; ++k)
-              if (kScalar || k < K)
-                acc[k] += (state_in_smem ? sm.W[size_t(k) * nf + i * kCT + tid] : Wg[size_t(k) * p + j]) * xj;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int k = 0; k < KT; ++k)
-            if (kScalar || k < K) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < KT; ++k)
-            if (kScalar || k < K) sm.red[fwarp * 32 + k] = acc[k];
-        }
-      }
-      __syncthreads();   // (1) warp sums visible; every thread is past step C of the previous update
-
-      // this update's step constants (functions of the deterministic wscale track), in the feature warps while the
-      // control warp exchanges: gamma / wscale, (beta gamma) / wscale with wscale as it will be after this step
-      double gw = 0.0, step = 0.0, thr = 0.0, ws_c = 0.0;
-      const double bgs = beta * gamma * 1.0;
-      if (!control) {
-        ws_c = ((wscale < kSmall) ? 1.0 : wscale) * r;
-        gw = gamma / ws_c;
-        step = gamma / ws_c * 1.0;
-        thr = bgs / ws_c;
-      }
-
-      if (issuer && issued < total) {      // refill the slot the previous update released
-        issue_row(issued, s_refill);
-        ++issued;
-        if (issued < total) s_refill = seq[issued];
-      }
-
-      // ---- B: CTA sum (8 warps ascending) -> every CTA; then the 8 CTA sums ascending; gradient (redundant per CTA)
-      if (control) {
-        if (lane < K) {
-          double tsum = 0.0;
-          for (int w = 0; w < 8; ++w) tsum += sm.red[w * 32 + lane];
-          const uint32_t my_slot = a_part + ((xpar * (kCluster + 1) + cta) * 32u + static_cast<uint32_t>(lane)) * 8u;
-          const uint32_t gm_slot = a_part + ((xpar * (kCluster + 1) + kCluster) * 32u + static_cast<uint32_t>(lane)) * 8u;
-#pragma unroll
-          for (uint32_t c = 0; c < kCluster; ++c) {
-            const uint32_t bar_c = map_to_cta(a_pbar + xpar * 8u, c);
-            st_async_f64(map_to_cta(my_slot, c), tsum, bar_c);
-            if (cta == 0) st_async_f64(map_to_cta(gm_slot, c), gm_mine, bar_c);
-          }
-        }
-        // this CTA expects (kCluster + 1) * K doubles per update on its own barrier: one local arrival arms the phase
-        if (lane == 0) mbar_expect_tx(&sm.pbar[xpar], static_cast<uint32_t>((kCluster + 1) * K * 8));
-        mbar_wait(&sm.pbar[xpar], xphase);
-        const double gm_val = (lane < K) ? sm.part[(xpar * (kCluster + 1) + kCluster) * 32 + lane] : 0.0;
-        const bool valid = lane < K;
-        double lp = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += sm.red[w][lane];
         if (valid) {
-          double dot = 0.0;
-          for (int c = 0; c < kCluster; ++c) dot += sm.part[(xpar * (kCluster + 1) + c) * 32 + lane];
-          lp = dot * wscale + b_reg;
+          const uint32_t a_sum = a_mine + xpar * kParStride, a_bar = a_pbar + xpar * 8u;
+#pragma unroll
+          for (uint32_t c = 0; c < kCluster; ++c)
+            if (c < nct) st_async_f64(map_to_cta(a_sum, c), tsum, map_to_cta(a_bar, c));
+          if (cta == 0) {
+            // part[xpar][kCluster][lane] (a_mine points into row cta == 0 here)
+#pragma unroll
+            for (uint32_t c = 0; c < kCluster; ++c)
+              if (c < nct) st_async_f64(map_to_cta(a_sum + kGmOffset, c), gm_cur, map_to_cta(a_bar, c));
+          }
         }
+        // this CTA expects (nct + 1) * K doubles per update on its own barrier: one local arrival arms the phase
+        if (lane == 0) mbar_expect_tx(&sm.pbar[xpar], (nct + 1u) * static_cast<uint32_t>(K) * 8u);
+        CLTRACE(1, true);
+        mbar_wait(&sm.pbar[xpar], xphase);
+        CLTRACE(2, true);
+        double dot = 0.0;
+#pragma unroll
+        for (int c = 0; c < kCluster; ++c)
+          if (c < static_cast<int>(nct)) dot += sm.part[xpar][c][lane];       // blocks beyond the design's features are exact zeros
+        const double gm_val = sm.part[xpar][kCluster][lane];
+        const double lp = dot * wscale + b_reg;
         double g;
         if (family == kMultinomial) {
-          const double yc = __shfl_sync(0xffffffffu, y_val, 0);
-          const double lse = lse_warp(lp, valid);
-          g = sgd_exp(lp - lse);
+          const double yc = __shfl_sync(kFull, y_cur, 0);
+          const double lse = lse_classes<KT>(lp, valid, lane);
+          g = sgd_exp_inrange(lp - lse);
           if (static_cast<unsigned>(lane) == static_cast<unsigned>(yc + 0.5)) g -= 1.0;
         } else if (family == kBinomial) {
-          g = 1.0 - y_val - 1.0 / (1.0 + sgd_exp(lp));
+          g = 1.0 - y_cur - 1.0 / (1.0 + sgd_exp(lp));
         } else {
-          g = lp - y_val;
+          g = lp - y_cur;
         }
+        const double gch = g - gm_val;
+        sm.gch[lane] = valid ? gch : 0.0;
+        CLTRACE(3, true);
+        bar_arrive_named(2);                                                // g_change is in gch[]
+        // ---- slack: the feature warps are in their coefficient step and next dot product
         if (valid) {
-          const double gch = g - gm_val;
-          if (cta == 0) f.gmem[size_t(s) * K + lane] = g;
+          if (cta == 0) f.gmem[size_t(s_cur) * K + lane] = g;
           if (fit_intercept) {
             const double gn = div_by_n(gch, nd, rn);
             gsi_reg += gn;
             b_reg -= gamma * (gsi_reg + gn);
           }
-          sm.gch[lane] = gch;
         }
-        if (s != prev_s) {
-          prev2_s = prev_s;
-          prev2_g = prev_g;
+        if (wscale < kSmall) wscale = 1.0;
+        wscale *= r;
+        if (issuer && tg + kCRing < total) {      // the slot this update's row sat in is free: every lane read it before barrier 1
+          issue_row(tg + kCRing, s_refill);
+          if (tg + kCRing + 1 < total) s_refill = seq[tg + kCRing + 1];
         }
-        prev_s = s;
-        prev_g = g;
+        s_cur = s_n1;
+        s_n1 = s_n2;
+        if (tg + 3 < total) s_n2 = seq[tg + 3];
+        if (valid && tg + 1 < total) {
+          y_cur = fetch_y(s_cur);
+          if (cta == 0) {
+            gm_cur = f.gmem[size_t(s_cur) * K + lane];
+            prefetch_l2(&f.gmem[size_t(s_n1) * K + lane]);
+          }
+          prefetch_l2(&f.yt[size_t(s_n1) * Ky]);
+        }
       }
-      if (wscale < kSmall) {
-        for (int i = 0; i < nch && !control; ++i) {
-          const int j = feature_of(i);
-          if (j < p)
-            for (int k = 0; k < K; ++k) {
-              if (state_in_smem) sm.W[size_t(k) * nf + i * kCT + tid] *= wscale;
-              else Wg[size_t(k) * p + j] *= wscale;
+    } else {
+      // ================================================================ feature warps
+      for (int64_t t = 0; t < n; ++t, ++tg) {
+        const int slot = static_cast<int>(tg & (kCRing - 1));
+        const uint32_t parity = static_cast<uint32_t>((tg / kCRing) & 1);
+        CLTRACE(4, fwarp == 0);
+        mbar_wait(&sm.full[slot], parity);
+        CLTRACE(5, fwarp == 0);
+        // ---- A: partial dot products of this lane (ascending j), warp butterfly by recursive halving, warp sums
+        double x[NCH];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) x[i] = (kLanes * i + jbase < p) ? sm.ring[slot][i][tid] : 0.0;
+        double acc[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            const double w = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+            acc[k] += w * x[i];
+          }
+        }
+        const double tot = Halving<KT, 16>::run(acc, lane);
+        constexpr int kShift = 5 - ilog2(KT);
+        if ((lane & ((1 << kShift) - 1)) == 0) sm.red[fwarp][lane >> kShift] = tot;
+        CLTRACE(6, fwarp == 0);
+        bar_arrive_named(1);
+        // this update's step constants (functions of the deterministic wscale track), while the control warp exchanges:
+        // gamma / wscale, (beta gamma) / wscale with wscale as it will be after this step
+        const bool reset = wscale < kSmall;
+        const double ws_c = (reset ? 1.0 : wscale) * r;
+        const double gw = gamma / ws_c;
+        const double step = gamma / ws_c * 1.0;
+        const double thr = bgs / ws_c;
+        CLTRACE(7, fwarp == 0 && thr != 12345.678);
+        bar_sync_named(2);                                                  // g_change is in gch[]
+        CLTRACE(8, fwarp == 0);
+        double gch[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) gch[k] = sm.gch[k];
+        if (reset) {      // src/saga-dense.h:166-170
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              if constexpr (kReg) Wr[i * KT + k] *= wscale;
+              else Ws[(k * NCH + i) * kCT + tid] *= wscale;
             }
         }
-        wscale = 1.0;
-      }
-      wscale *= r;
-      __syncthreads();   // (2) g_change visible
-
-      // ---- C: fused coefficient step, prox, gradient-average update on the owned features
-      // (src/saga-dense.h:176-183; penalty functors src/penalties.h:27-79 with scaling = 1)
-      double gch[KT];
+        wscale = ws_c;
+        // ---- C: fused coefficient step, prox, gradient-average update on the owned features
+        // (src/saga-dense.h:176-183; penalty functors src/penalties.h:27-79 with scaling = 1). Slots beyond p and classes
+        // beyond K hold zeros and stay zeros under these operations.
 #pragma unroll
-      for (int k = 0; k < KT; ++k) gch[k] = (kScalar || k < K) ? sm.gch[k] : 0.0;
-      for (int i = 0; i < nch && !control; ++i) {
-        const int j = feature_of(i);
-        if (j >= p) continue;
-        const double xj = xr[i * kCT + tid];
-        double w[KT], gs[KT];
-        double sq = 0.0;
+        for (int i = 0; i < NCH; ++i) {
+          double w[KT], gs[KT], gnew[KT];
+          double sq = 0.0;
+          bool rare = false;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          if (kScalar || k < K) {
-            double* Wp = state_in_smem ? &sm.W[size_t(k) * nf + i * kCT + tid] : &Wg[size_t(k) * p + j];
-            double* Gp = state_in_smem ? &sm.G[size_t(k) * nf + i * kCT + tid] : &Gg[size_t(k) * p + j];
-            gs[k] = *Gp;
-            const double gx = gch[k] * xj;
-            const double v = (*Wp - gx * gw) - step * gs[k];
+          for (int k = 0; k < KT; ++k) {
+            const double w_in = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+            gs[k] = kReg ? Gr[i * KT + k] : Gs[(k * NCH + i) * kCT + tid];
+            const double gx = gch[k] * x[i];
+            const double v = (w_in - gx * gw) - step * gs[k];
             w[k] = (PEN == kElasticNet) ? soft_threshold(v, thr) : v;
             if (PEN == kGroupLasso) sq += v * v;
-            *Gp = gs[k] + div_by_n(gx, nd, rn);
+            gnew[k] = gs[k] + div_by_n_flag(gx, nd, rn, rare);
+          }
+          if (__builtin_expect(rare, 0)) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) gnew[k] = gs[k] + (gch[k] * x[i]) / nd;
+          }
+          if (PEN == kGroupLasso) {
+            const double factor = bgs / sqrt(sq);
+            const double mult = 1.0 - factor / ws_c;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            if constexpr (kReg) {
+              Wr[i * KT + k] = w[k];
+              Gr[i * KT + k] = gnew[k];
+            } else {
+              Ws[(k * NCH + i) * kCT + tid] = w[k];
+              Gs[(k * NCH + i) * kCT + tid] = gnew[k];
+            }
           }
         }
-        if (PEN == kGroupLasso) {
-          const double factor = bgs / sqrt(sq);
-          const double mult = 1.0 - factor / ws_c;
-#pragma unroll
-          for (int k = 0; k < KT; ++k)
-            if (kScalar || k < K) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < KT; ++k)
-          if (kScalar || k < K) {
-            if (state_in_smem) sm.W[size_t(k) * nf + i * kCT + tid] = w[k];
-            else Wg[size_t(k) * p + j] = w[k];
-          }
+        CLTRACE(9, fwarp == 0);
       }
     }
 
     // ---- epoch end: unscale, convergence over the whole cluster (src/saga-dense.h:188-208, src/utils.h:240-262)
     double mc = 0.0, ms = 0.0;
-    for (int i = 0; i < nch && !control; ++i) {
-      const int j = feature_of(i);
-      if (j >= p) continue;
-      for (int k = 0; k < K; ++k) {
-        const size_t e = size_t(k) * p + j;
-        double* Wp = state_in_smem ? &sm.W[size_t(k) * nf + i * kCT + tid] : &Wg[e];
-        const double w = *Wp * wscale;
-        *Wp = w;
-        mc = fmax(mc, fabs(w - f.Wprev[e]));
-        ms = fmax(ms, fabs(w));
-        f.Wprev[e] = w;
+    if (!control) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int j = kLanes * i + jbase;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (j < p && k < K) {
+            const size_t e = size_t(k) * p + j;
+            const double w_in = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+            const double w = w_in * wscale;
+            if constexpr (kReg) Wr[i * KT + k] = w;
+            else Ws[(k * NCH + i) * kCT + tid] = w;
+            mc = fmax(mc, fabs(w - f.Wprev[e]));
+            ms = fmax(ms, fabs(w));
+            f.Wprev[e] = w;
+          }
+        }
+      }
+      mc = warp_max(mc);
+      ms = warp_max(ms);
+      if (lane == 0) {
+        sm.cred[fwarp][0] = mc;
+        sm.cred[fwarp][1] = ms;
       }
     }
     wscale = 1.0;
-    mc = warp_max(mc);
-    ms = warp_max(ms);
-    __syncthreads();       // red[] is free again
-    if (lane == 0 && !control) {
-      sm.red[fwarp * 32] = mc;
-      sm.red[fwarp * 32 + 1] = ms;
-    }
     __syncthreads();
     const uint32_t epar = static_cast<uint32_t>(ep & 1), ephase = static_cast<uint32_t>((ep >> 1) & 1);
     if (threadIdx.x == 0) {
       double mc_c = 0.0, ms_c = 0.0;
       for (int w = 0; w < 8; ++w) {
-        mc_c = fmax(mc_c, sm.red[w * 32]);
-        ms_c = fmax(ms_c, sm.red[w * 32 + 1]);
+        mc_c = fmax(mc_c, sm.cred[w][0]);
+        ms_c = fmax(ms_c, sm.cred[w][1]);
       }
-      const uint32_t a_conv = smem_u32(sm.conv) + ((epar * kCluster + cta) * 2u) * 8u;
-      for (uint32_t c = 0; c < kCluster; ++c) {
-        st_cluster_f64(map_to_cta(a_conv, c), mc_c);
-        st_cluster_f64(map_to_cta(a_conv + 8u, c), ms_c);
-        arrive_cluster(map_to_cta(smem_u32(sm.cbar) + epar * 8u, c));
+      const uint32_t a_conv = smem_u32(&sm.conv[epar][cta][0]);
+      const uint32_t a_cbar = smem_u32(&sm.cbar[epar]);
+      for (uint32_t c = 0; c < nct; ++c) {
+        const uint32_t bar_c = map_to_cta(a_cbar, c);
+        st_async_f64(map_to_cta(a_conv, c), mc_c, bar_c);
+        st_async_f64(map_to_cta(a_conv + 8u, c), ms_c, bar_c);
       }
+      mbar_expect_tx(&sm.cbar[epar], nct * 16u);
     }
-    wait_cluster(&sm.cbar[epar], ephase);
+    mbar_wait(&sm.cbar[epar], ephase);
     double mc_all = 0.0, ms_all = 0.0;
-    for (int c = 0; c < kCluster; ++c) {
-      mc_all = fmax(mc_all, sm.conv[(epar * kCluster + c) * 2]);
-      ms_all = fmax(ms_all, sm.conv[(epar * kCluster + c) * 2 + 1]);
+    for (int c = 0; c < static_cast<int>(nct); ++c) {
+      mc_all = fmax(mc_all, sm.conv[epar][c][0]);
+      ms_all = fmax(ms_all, sm.conv[epar][c][1]);
     }
-    __syncthreads();
     const bool all_zero = (ms_all == 0.0) && (mc_all == 0.0);
     const bool no_change = (ms_all != 0.0) && (mc_all / ms_all <= f.tol);
     ++it_outer;
@@ -489,21 +575,24 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
 
   // drain copies that were issued but never consumed (early stop) before the shared memory goes away
   if (issuer)
-    for (int64_t q = tg; q < issued; ++q)
-      mbar_wait(&sm.full[static_cast<int>(q % kCRing)], static_cast<uint32_t>((q / kCRing) & 1));
+    for (int64_t q = tg; q < tg + kCRing && q < total; ++q)
+      mbar_wait(&sm.full[static_cast<int>(q & (kCRing - 1))], static_cast<uint32_t>((q / kCRing) & 1));
   __syncthreads();
 
-  if (state_in_smem && !control) {
-    for (int i = 0; i < nch; ++i) {
-      const int j = feature_of(i);
-      if (j >= p) continue;
-      for (int k = 0; k < K; ++k) {
-        Wg[size_t(k) * p + j] = sm.W[size_t(k) * nf + i * kCT + tid];
-        Gg[size_t(k) * p + j] = sm.G[size_t(k) * nf + i * kCT + tid];
+  if (!control) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int j = kLanes * i + jbase;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        if (j < p && k < K) {
+          Wg[size_t(k) * p + j] = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+          Gg[size_t(k) * p + j] = kReg ? Gr[i * KT + k] : Gs[(k * NCH + i) * kCT + tid];
+        }
       }
     }
   }
-  if (cta == 0 && owner) {
+  if (cta == 0 && valid) {
     f.b[lane] = b_reg;
     f.gsi[lane] = gsi_reg;
   }
@@ -523,41 +612,83 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   }
 }
 
-template <int KT, int PEN>
-static cudaError_t launch_cluster_variant(size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(saga_dense_cluster_kernel<KT, PEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(kCluster, 1, 1);
-  cfg.blockDim = dim3(kCBlock, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, saga_dense_cluster_kernel<KT, PEN>, fit, prog, ra);
+template <int KT, int NCH>
+constexpr size_t cluster_smem(void) {
+  return sizeof(ClusterFixed<NCH>) + (cluster_reg_state(KT, NCH) ? 0 : sizeof(double) * 2 * size_t(KT) * NCH * kCT);
 }
 
-template <int KT>
-static cudaError_t launch_cluster_kt(int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
-  switch (pen) {
-    case kRidge: return launch_cluster_variant<KT, kRidge>(smem, fit, prog, ra, st);
-    case kElasticNet: return launch_cluster_variant<KT, kElasticNet>(smem, fit, prog, ra, st);
-    default: return launch_cluster_variant<KT, kGroupLasso>(smem, fit, prog, ra, st);
+inline int nch_bucket(int p) {
+  const int nch = (p + kLanes - 1) / kLanes;
+  return nch <= 1 ? 1 : (nch <= 2 ? 2 : (nch <= 4 ? 4 : 0));
+}
+inline size_t fast_smem_bytes(int kt, int nch) {
+  const size_t fixed = nch == 1 ? sizeof(ClusterFixed<1>) : (nch == 2 ? sizeof(ClusterFixed<2>) : sizeof(ClusterFixed<4>));
+  return fixed + (cluster_reg_state(kt, nch) ? 0 : sizeof(double) * 2 * size_t(kt) * nch * kCT);
+}
+// the compile-time instantiations cover slice counts 1, 2, 4 whose state fits the registers or the shared memory
+inline bool fast_eligible(int K, int p) {
+  const int nch = nch_bucket(p);
+  return nch != 0 && fast_smem_bytes(dense_kt_bucket(K), nch) <= dense_smem_budget();
+}
+
+template <int KT, int PEN, int NCH>
+cudaError_t launch_cluster_variant(int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  constexpr size_t smem = cluster_smem<KT, NCH>();
+  if constexpr (smem > 227 * 1024) {
+    return cudaErrorInvalidConfiguration;       // not reachable: fast_eligible() sends these shapes to the generic kernel
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(saga_dense_cluster_kernel<KT, PEN, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nct, 1, 1);
+    cfg.blockDim = dim3(kCBlock, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nct;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, saga_dense_cluster_kernel<KT, PEN, NCH>, fit, prog, ra);
   }
 }
 
-cudaError_t launch_saga_dense_cluster(int K, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+template <int KT, int PEN>
+cudaError_t launch_cluster_nch(int nch, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  switch (nch) {
+    case 1: return launch_cluster_variant<KT, PEN, 1>(nct, fit, prog, ra, st);
+    case 2: return launch_cluster_variant<KT, PEN, 2>(nct, fit, prog, ra, st);
+    default: return launch_cluster_variant<KT, PEN, 4>(nct, fit, prog, ra, st);
+  }
+}
+
+template <int KT>
+cudaError_t launch_cluster_kt(int pen, int nch, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  switch (pen) {
+    case kRidge: return launch_cluster_nch<KT, kRidge>(nch, nct, fit, prog, ra, st);
+    case kElasticNet: return launch_cluster_nch<KT, kElasticNet>(nch, nct, fit, prog, ra, st);
+    default: return launch_cluster_nch<KT, kGroupLasso>(nch, nct, fit, prog, ra, st);
+  }
+}
+
+}  // namespace
+
+size_t dense_cluster_smem_bytes(int K, int p) {
+  return fast_eligible(K, p) ? fast_smem_bytes(dense_kt_bucket(K), nch_bucket(p)) : dense_cluster_generic_smem_bytes(K, p);
+}
+
+cudaError_t launch_saga_dense_cluster(int K, int p, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  if (!fast_eligible(K, p)) return launch_saga_dense_cluster_generic(K, pen, smem, fit, prog, ra, st);
+  const int nch = nch_bucket(p);
+  const int nct = p <= 2 * kCT ? 2 : (p <= 4 * kCT ? 4 : kCluster);     // CTAs that own features; absent blocks are exact zeros
   switch (dense_kt_bucket(K)) {
-    case 1: return launch_cluster_kt<1>(pen, smem, fit, prog, ra, st);
-    case 4: return launch_cluster_kt<4>(pen, smem, fit, prog, ra, st);
-    case 8: return launch_cluster_kt<8>(pen, smem, fit, prog, ra, st);
-    case 16: return launch_cluster_kt<16>(pen, smem, fit, prog, ra, st);
-    default: return launch_cluster_kt<32>(pen, smem, fit, prog, ra, st);
+    case 1: return launch_cluster_kt<1>(pen, nch, nct, fit, prog, ra, st);
+    case 4: return launch_cluster_kt<4>(pen, nch, nct, fit, prog, ra, st);
+    case 8: return launch_cluster_kt<8>(pen, nch, nct, fit, prog, ra, st);
+    case 16: return launch_cluster_kt<16>(pen, nch, nct, fit, prog, ra, st);
+    default: return launch_cluster_kt<32>(pen, nch, nct, fit, prog, ra, st);
   }
 }
 

@@ -103,3 +103,33 @@ def test_late_lane_butterfly_identity():
         for i in range(5):
             closed = closed + rc[i, lane]
         assert closed == full[0]
+
+
+def test_lazy_virtual_centring_does_not_preserve_the_reference_bits():
+    """SURVEY.md section 8f-4 (H2) asked for an "exact lazy form" of sparse + standardize = TRUE: keep a running scalar
+    for the dense correction a.row(k) -= x_center_scaled * g_change(k) * scaling that AddWeighted applies to EVERY
+    feature on EVERY update (reference src/saga-sparse.h:127-128), and apply it just in time when a feature is next
+    gathered. The reference rounds w_j after each of those T subtractions; the lazy form subtracts c_j * sum_t(...) once.
+    Those are different IEEE operation sequences, and they do give different bits (so do the two dot products
+    w . x_center_scaled of :276-277 taken over a lazily and an eagerly corrected w). Supports and path lengths are
+    decided at that level (include/sgdnet_arith.h), so the library keeps the reference's per-update sweeps for this
+    mode (saga_sparse_generic_kernel) instead of a lazy form that would only be tolerance-equal. This test is the
+    counterexample that decision rests on."""
+    rng = np.random.default_rng(11)
+    T, p = 64, 4096
+    c = rng.normal(size=p)
+    w0 = rng.normal(size=p)
+    gch = rng.normal(size=T) * 1e-2
+    gamma, r = 0.3, 1.0 - 1e-4
+    wscale = 1.0
+    eager = w0.copy()
+    run = 0.0
+    for t in range(T):
+        wscale *= r
+        scaling = -gamma / wscale
+        eager -= c * gch[t] * scaling                       # (x_center_scaled * g_change(k)) * scaling, then -=
+        run += gch[t] * scaling
+    lazy = w0 - c * run
+    differ = np.mean(eager != lazy)
+    assert differ > 0.5                                     # most elements end with different bits
+    np.testing.assert_allclose(lazy, eager, rtol=0, atol=1e-13)    # while agreeing to rounding level

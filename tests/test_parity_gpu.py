@@ -74,6 +74,31 @@ def test_dense_wide_designs_on_the_cluster_kernel(cuda, oracle, family, K, alpha
         assert_fit_parity(g.raw, r.raw)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,K,p,alpha", [("multinomial", 20, 600, 0.7),      # 32-class bucket, one slice: state in shared memory
+                                              ("mgaussian", 8, 5000, 1.0),        # 8-class bucket, four slices: state in shared memory
+                                              ("multinomial", 6, 3000, 0.5),      # 8-class bucket, two slices: state in registers
+                                              ("gaussian", 1, 7000, 0.3),         # scalar, four slices: state in registers
+                                              ("binomial", 1, 2048, 1.0),         # exactly one full slice per CTA
+                                              ("mgaussian", 2, 9000, 0.5),        # five slices: the any-shape cluster kernel
+                                              ("multinomial", 12, 4500, 0.0)])    # state too large for shared memory: the any-shape kernel
+def test_dense_cluster_kernel_instantiations(cuda, oracle, family, K, p, alpha):
+    """Every state placement / slice count of saga_dense_cluster.cu and the fallback to saga_dense_cluster_generic.cu."""
+    rng = np.random.default_rng(23)
+    n = 120
+    x = rng.normal(size=(n, p)) * (rng.uniform(size=(n, p)) < 0.2)
+    if family == "multinomial":
+        y = np.argmax(x[:, :K] + rng.gumbel(size=(n, K)), axis=1)
+    elif family == "mgaussian":
+        y = x[:, :5] @ rng.normal(size=(5, K)) + 0.5 * rng.normal(size=(n, K))
+    elif family == "binomial":
+        y = (x[:, 0] - x[:, 1] + rng.normal(size=n) > 0).astype(float)
+    else:
+        y = x[:, :4] @ np.array([1.0, -2.0, 0.5, 3.0]) + rng.normal(size=n)
+    g, r = both(cuda, oracle, x, y, family=family, alpha=alpha, nlambda=4, thresh=1e-3, maxit=12, seed=5)
+    assert_fit_parity(g.raw, r.raw)
+
+
 def _heart():
     d = golden("heart")
     n, p = (int(v) for v in d["x_shape"])
