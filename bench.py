@@ -323,19 +323,32 @@ def part_dense(lib):
     return out
 
 
-def part_passes(lib, sess, n, nnz, peak):
-    """The per-lambda deviance pass (loss_pass_kernel + finish_lambda_kernel) on config 2's design: CUDA-event time of
-    sgdnet_session_finish_lambda; algorithmic bytes 12*nnz + 16*n + 8*n."""
+def part_passes(lib, sess, n, nnz, peak, rng):
+    """The per-lambda deviance pass (rescale + loss pass + finish_lambda kernels) on config 2's design: CUDA-event time of
+    sgdnet_session_finish_lambda; algorithmic bytes 12*nnz + 16*n + 8*n. Two states of the coefficients:
+    as a lasso path sees them (few nonzero weights: the nonzero bitmap filters the gathers and the pass streams X at HBM
+    speed) and all weights live (one 8-byte gather per nonzero of X: bound by the LSU's one gather wavefront per cycle
+    per SM, 148 x 1.965 GHz x 12 B = 3.5 TB/s of algorithmic bytes at most)."""
     ms = C.c_float(0)
-    times = []
-    for _ in range(6):
-        lib.check(lib.sym("session_finish_lambda")(sess, 30, C.byref(ms)), "finish_lambda")
-        times.append(ms.value)
-    t = float(np.median(times[1:])) * 1e-3
     bytes_pass = 12 * nnz + 16 * n + 8 * n
-    return {"deviance_pass": {"kernel": "loss_pass_kernel (+ finish_lambda_kernel)", "bound": "hbm", "achieved": bytes_pass / t / 1e9,
-                              "peak": peak, "unit": "GB/s", "frac": bytes_pass / t / 1e9 / peak, "launch_ms": t * 1e3,
-                              "bytes_per_pass": bytes_pass, "workload": "config 2 design (1M x 100k, 1e8 nonzeros), one lambda"}}
+
+    def timed(lambda_ind):
+        times = []
+        for _ in range(6):
+            lib.check(lib.sym("session_finish_lambda")(sess, lambda_ind, C.byref(ms)), "finish_lambda")
+            times.append(ms.value)
+        return float(np.median(times[1:])) * 1e-3
+
+    def entry(t, state):
+        return {"kernel": "rescale_kernel + loss_pass_tiles_kernel + finish_lambda_kernel", "bound": "hbm", "achieved": bytes_pass / t / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": bytes_pass / t / 1e9 / peak, "launch_ms": t * 1e3, "bytes_per_pass": bytes_pass,
+                "workload": "config 2 design (1M x 100k, 1e8 nonzeros), one lambda; " + state}
+    out = {"deviance_pass_all_weights_live": entry(timed(30), "coefficients after the timed epochs at lambda[30] from a cold start "
+                                                              "(nearly every weight nonzero: gather-bound)")}
+    # a state as the warm-started path sees it: a few epochs at a strong penalty zero most weights
+    lib.check(lib.sym("session_run_epochs")(sess, 3, 3, C.byref(rng), C.byref(ms)), "run_epochs")
+    out["deviance_pass"] = entry(timed(3), "coefficients after 3 further epochs at lambda[3] (lasso-sparse weights, as along the path)")
+    return out
 
 
 def part_cpu_cv(args):
@@ -465,7 +478,7 @@ def main():
 
     roofline_passes = None
     if "passes" not in args.skip and world == 1:
-        roofline_passes = part_passes(lib, sess, n, int(m.p[-1]), peak)
+        roofline_passes = part_passes(lib, sess, n, int(m.p[-1]), peak, rng)
     lib.sym("session_destroy")(sess)
 
     # ---------------- e2e: sgdnet_fit_sparse with host buffers

@@ -218,6 +218,7 @@ struct FitJob {
   bool needs_finish = false;          // the last solver launch ended a lambda (or, debug mode, an epoch): passes are due
   bool stale_prep = false;            // a prepared launch was discarded; its kernels may still be running on st_prep
   int loss_blocks = 1;
+  int loss_tiles = 0;                 // > 0: CTAs of the bulk-copy tile form of the loss pass (sparse K == 1)
   int mask_words = 0;                 // sparse K == 1: words of the nonzero-coefficient bitmap (0: p too large for it)
   size_t dense_smem = 0;
   bool dense_cluster = false;         // wide dense design: the cluster kernel (saga_dense_cluster.cu)
@@ -247,6 +248,7 @@ struct Engine {
   bool trace_rounds = std::getenv("SGDNET_TRACE_ROUNDS") != nullptr;   // per-launch device times on stderr
   bool host_rng = std::getenv("SGDNET_HOST_RNG") != nullptr;           // draw MT indices on the host (development aid)
   bool no_overlap = std::getenv("SGDNET_NO_PREP_OVERLAP") != nullptr;  // prepare a launch only when it is due
+  bool no_loss_tiles = std::getenv("SGDNET_NO_LOSS_TILES") != nullptr;   // loss pass without the bulk-copy tile form (measurement aid)
   double seconds_setup = 0.0;
   double t_begin = 0.0, t_run = 0.0;
   size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set aside for persisting lines (0: not available / switched off)
@@ -572,7 +574,12 @@ struct Engine {
     f.partials = arena.alloc<double>(job.loss_blocks);
     f.xb_partials = arena.alloc<double>(size_t(kRescaleBlocks) * K);
     const int mask_words = (p + 31) / 32;
-    job.mask_words = (job.variant == Variant::SparseK1 && mask_words * 4 <= 40 * 1024) ? mask_words : 0;
+    // sparse, K == 1, no virtual centring: the bulk-copy tile form of the loss pass, one CTA per SM
+    job.loss_tiles = job.variant == Variant::SparseK1
+                         ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(sms, job.loss_blocks), (d.n + 31) / 32)))
+                         : 0;
+    if (no_loss_tiles) job.loss_tiles = 0;
+    job.mask_words = (job.variant == Variant::SparseK1 && mask_words <= loss_mask_words_max(job.loss_tiles > 0)) ? mask_words : 0;
     f.nz_mask = job.mask_words ? arena.alloc<uint32_t>(mask_words) : nullptr;
     job.dense_cluster = job.variant == Variant::Dense && p >= SGD_WIDE_P;
     if (job.dense_cluster) {
@@ -841,10 +848,10 @@ struct Engine {
     j.t_finish = now_s();
     if (use_events()) CK(cudaEventRecord(j.ev_f0, j.st));
     if (j.dev.debug) {
-      CK(launch_epoch_loss(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.st));
+      CK(launch_epoch_loss(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.loss_tiles, j.st));
       j.launches += 2;
     }
-    CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.mask_words, j.round_id, j.st));
+    CK(launch_finish_lambda(j.dev_ptr, j.prog_ptr, j.loss_blocks, j.loss_tiles, j.mask_words, j.round_id, j.st));
     j.launches += 3;
     if (use_events()) CK(cudaEventRecord(j.ev_f1, j.st));
     j.phase = Phase::Finish;

@@ -53,8 +53,10 @@ void mt_indices_host(const MtState* src, uint32_t n, int n_epochs, uint32_t* seq
 // passes.cu
 cudaError_t launch_lag_scaling(FitDev* fit, Progress* prog, cudaStream_t st);
 // mask_words: 32-bit words of the nonzero-coefficient bitmap the deviance pass may stage in shared memory (0: none)
-cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int mask_words, uint32_t round_id, cudaStream_t st);
-cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st);
+// tiles > 0 (sparse, K == 1, no virtual centring): the bulk-copy tile form of the loss pass on that many CTAs
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int tiles, int mask_words, uint32_t round_id, cudaStream_t st);
+cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, int tiles, cudaStream_t st);
+int loss_mask_words_max(bool tiles);
 
 struct PredictArgs {
   int32_t sparse, family, K, Ky, p, ld, n_lambda, measure;   // measure: SGDNET_MEASURE_* (include/sgdnet_b200.h)

@@ -155,6 +155,217 @@ __device__ __forceinline__ double loss_tiles_sparse_k1(const FitDev& f, int mode
   return acc;
 }
 
+// ---- The same pass with the design streamed by bulk copies (configs 2 and 5 at size): one persistent CTA per SM, a
+// producer warp and 16 consumer warps around a 4-stage shared-memory ring of 32-row tiles. The rows of a tile are
+// consecutive in the padded CSR, so a tile's index run and value run are ONE contiguous range each: two 1-D bulk
+// copies (cp.async.bulk -> UBLKCP, complete_tx on the stage's mbarrier) of about 13 KB + 26 KB bring them in, three
+// tiles ahead of the warps that consume them - about 115 KB in flight per SM without a register or an L1 line spent
+// on it. The producer derives each row's offset inside the tile from the 32 row descriptors it reads (a warp scan; the
+// descriptors themselves are fetched two tiles ahead, so a freed stage is refilled at once) and leaves it, with the
+// row's response, in the stage. A consumer warp takes two rows of every tile, interleaved:
+// position e of a row goes to the running sum of lane e mod 32, then the xor butterfly - the solver's association
+// (sgdnet_arith.h item 2). Linear predictors and responses collect one per lane over 16 tiles, so exp / log of the
+// loss run once per 32 rows per warp. Partial sums: per lane over its rows in order, butterfly per warp, warps in order
+// per block, blocks in order (finish_lambda_kernel) - fixed, hence reproducible.
+// A tile that is not one contiguous range or has more than kTileCap padded entries (very long rows) is read straight
+// from global memory by the consumers (kind 1).
+constexpr int kTileRows = 32;
+constexpr int kTileCap = 3584;          // padded entries per staged tile
+constexpr int kTileStages = 4;
+constexpr int kTileWarps = 16;          // consumer warps; warp kTileWarps is the producer
+constexpr int kTileThreads = (kTileWarps + 1) * 32;
+
+struct __align__(16) TileRow {
+  int64_t start;        // first entry of the row in ci / cv
+  int32_t off;          // first entry of the row inside the staged tile
+  int32_t nnz;
+};
+struct __align__(128) TileStage {
+  double cv[kTileCap];
+  int32_t ci[kTileCap];
+  TileRow row[kTileRows];
+  double y[kTileRows];
+  int32_t kind;         // 0: staged, 1: read the rows from global memory
+  int32_t pad_[31];
+};
+struct __align__(128) TileSmem {
+  TileStage st[kTileStages];
+  uint64_t full[kTileStages];
+  uint64_t empty[kTileStages];
+  double red[kTileWarps];
+};
+
+size_t loss_tiles_fixed_smem() { return sizeof(TileSmem); }
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+loss_pass_tiles_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode, int mask_words) {
+  extern __shared__ __align__(128) unsigned char tile_smem_raw[];
+  const Progress& pg = *prog;
+  const FitDev& f = *fit;
+  if (mode == 0 ? (pg.status != kLambdaDone) : !f.debug) return;
+  TileSmem& sm = *reinterpret_cast<TileSmem*>(tile_smem_raw);
+  uint32_t* const nz_smem = reinterpret_cast<uint32_t*>(tile_smem_raw + sizeof(TileSmem));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = f.n;
+  const int p = f.p;
+  const int words = (p + 31) / 32;
+  const bool use_mask = mode == 0 && f.nz_mask != nullptr && mask_words >= words;
+  if (tid == 0) {
+    for (int i = 0; i < kTileStages; ++i) {
+      mbar_init(&sm.full[i], 1);
+      mbar_init(&sm.empty[i], kTileWarps);
+    }
+    fence_barrier_init();
+  }
+  if (use_mask)
+    for (int i = tid; i < words; i += kTileThreads) nz_smem[i] = f.nz_mask[i];
+  __syncthreads();
+
+  const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+  const RowInfo* __restrict__ rows = f.rows;
+  const int32_t* __restrict__ ci = f.ci;
+  const double* __restrict__ cv = f.cv;
+  double acc = 0.0;
+
+  if (warp == kTileWarps) {
+    // ------------------------------------------------------------ producer
+    int it = 0;
+    auto fetch = [&](int64_t tile, RowInfo& ri, double& y) {
+      const int64_t s = tile * kTileRows + lane;
+      ri = RowInfo{};
+      y = 0.0;
+      if (tile < n_tiles && s < n) {
+        ri = rows[s];
+        y = f.yt[s];
+      }
+    };
+    RowInfo ri_a, ri_b;
+    double y_a, y_b;
+    fetch(blockIdx.x, ri_a, y_a);
+    fetch(int64_t(blockIdx.x) + gridDim.x, ri_b, y_b);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int stage = it % kTileStages;
+      const RowInfo ri = ri_a;
+      const double y = y_a;
+      ri_a = ri_b;
+      y_a = y_b;
+      fetch(tile + 2 * int64_t(gridDim.x), ri_b, y_b);
+      if (it >= kTileStages) mbar_wait(&sm.empty[stage], static_cast<uint32_t>((it / kTileStages - 1) & 1));
+      const bool have = tile * kTileRows + lane < n;
+      const int padded = (ri.nnz + 3) & ~3;
+      int incl = padded;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int64_t start0 = __shfl_sync(0xffffffffu, ri.start, 0);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const bool in_place = !have || ri.nnz == 0 || ri.start == start0 + (incl - padded);
+      const bool staged = __all_sync(0xffffffffu, in_place) && total <= kTileCap;
+      TileStage& st = sm.st[stage];
+      st.row[lane] = TileRow{ri.start, incl - padded, have ? ri.nnz : 0};
+      st.y[lane] = y;
+      if (lane == 0) st.kind = staged ? 0 : 1;
+      __syncwarp();
+      if (lane == 0) {
+        if (staged && total > 0) {
+          mbar_expect_tx(&sm.full[stage], static_cast<uint32_t>(total) * 12u);
+          bulk_g2s(st.ci, ci + start0, static_cast<uint32_t>(total) * 4u, &sm.full[stage]);
+          bulk_g2s(st.cv, cv + start0, static_cast<uint32_t>(total) * 8u, &sm.full[stage]);
+        } else {
+          mbar_arrive(&sm.full[stage]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumers: rows 2 * warp, 2 * warp + 1 of every tile
+    const double* __restrict__ W = f.W;
+    const double b0 = f.b[0];
+    const int family = f.family;
+    const double nd = static_cast<double>(static_cast<uint32_t>(n));
+    double lp_mine = 0.0, y_mine = 0.0;
+    bool row_mine = false;
+    int it = 0, held = 0;
+    auto flush = [&]() {
+      double loss = row_mine ? loss_scalar(family, lp_mine + b0, y_mine) : 0.0;
+      if (mode == 1) loss = loss / nd;
+      acc += loss;
+      row_mine = false;
+      held = 0;
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int stage = it % kTileStages;
+      mbar_wait(&sm.full[stage], static_cast<uint32_t>((it / kTileStages) & 1));
+      const TileStage& st = sm.st[stage];
+      const TileRow ra = st.row[2 * warp], rb = st.row[2 * warp + 1];
+      double a0 = 0.0, a1 = 0.0;
+      const int nmax = ra.nnz > rb.nnz ? ra.nnz : rb.nnz;
+      const bool staged = st.kind == 0;
+      // warp-uniform trip count (four 32-entry chunks of both rows per pass, predicated per lane): eight independent
+      // index -> bitmap -> gather chains in flight
+      auto two_rows = [&](const int32_t* __restrict__ cia, const int32_t* __restrict__ cib, const double* __restrict__ cva,
+                          const double* __restrict__ cvb) {
+#pragma unroll 1
+        for (int e0 = 0; e0 < nmax; e0 += 128) {
+          int ja[4], jb[4];
+          double va[4], vb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 32 * u + lane;
+            const bool oka = e < ra.nnz, okb = e < rb.nnz;
+            ja[u] = oka ? cia[e] : -1;
+            jb[u] = okb ? cib[e] : -1;
+            va[u] = oka ? cva[e] : 0.0;
+            vb[u] = okb ? cvb[e] : 0.0;
+          }
+          double wa[4], wb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool la = ja[u] >= 0 && (!use_mask || ((nz_smem[ja[u] >> 5] >> (ja[u] & 31)) & 1u));
+            const bool lb = jb[u] >= 0 && (!use_mask || ((nz_smem[jb[u] >> 5] >> (jb[u] & 31)) & 1u));
+            wa[u] = la ? __ldg(W + ja[u]) : 0.0;
+            wb[u] = lb ? __ldg(W + jb[u]) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double a0n = a0 + va[u] * wa[u], a1n = a1 + vb[u] * wb[u];
+            a0 = ja[u] >= 0 ? a0n : a0;
+            a1 = jb[u] >= 0 ? a1n : a1;
+          }
+        }
+      };
+      if (staged) two_rows(st.ci + ra.off, st.ci + rb.off, st.cv + ra.off, st.cv + rb.off);     // shared memory (LDS)
+      else two_rows(ci + ra.start, ci + rb.start, cv + ra.start, cv + rb.start);                 // global memory
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      }
+      // lane 2 * held + r keeps row r of this tile
+      const int64_t s_mine = tile * kTileRows + 2 * warp + (lane & 1);
+      if ((lane >> 1) == held) {
+        lp_mine = (lane & 1) ? a1 : a0;
+        y_mine = st.y[2 * warp + (lane & 1)];
+        row_mine = s_mine < n;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+      if (++held == 16) flush();
+    }
+    if (held > 0) flush();
+    acc = warp_sum(acc);
+    if (lane == 0) sm.red[warp] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int w = 0; w < kTileWarps; ++w) a += sm.red[w];
+    f.partials[blockIdx.x] = a;
+  }
+}
+
 __global__ void __launch_bounds__(kPassThreads)
 loss_pass_kernel(FitDev* __restrict__ fit, const Progress* __restrict__ prog, int mode, int mask_words) {
   __shared__ double wc_s[32];
@@ -335,14 +546,30 @@ finish_lambda_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, int 
   }
 }
 
-cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int mask_words, uint32_t round_id, cudaStream_t st) {
+// `tiles` > 0: the fit is sparse, K == 1, without virtual centring - the bulk-copy form on that many CTAs (<= blocks)
+static cudaError_t launch_loss(FitDev* fit, Progress* prog, int blocks, int tiles, int mode, int mask_words, cudaStream_t st) {
+  if (tiles > 0) {
+    const size_t smem = loss_tiles_fixed_smem() + size_t(mask_words) * 4;
+    cudaError_t e = cudaFuncSetAttribute(loss_pass_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    loss_pass_tiles_kernel<<<tiles, kTileThreads, smem, st>>>(fit, prog, mode, mask_words);
+  } else {
+    loss_pass_kernel<<<blocks, kPassThreads, size_t(mask_words) * 4, st>>>(fit, prog, mode, mask_words);
+  }
+  return cudaGetLastError();
+}
+
+int loss_mask_words_max(bool tiles) {
+  return tiles ? static_cast<int>((227 * 1024 - loss_tiles_fixed_smem()) / 4) : 40 * 1024 / 4;
+}
+
+cudaError_t launch_finish_lambda(FitDev* fit, Progress* prog, int blocks, int tiles, int mask_words, uint32_t round_id, cudaStream_t st) {
   rescale_kernel<<<kRescaleBlocks, kPassThreads, 0, st>>>(fit, prog);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  loss_pass_kernel<<<blocks, kPassThreads, size_t(mask_words) * 4, st>>>(fit, prog, 0, mask_words);
-  e = cudaGetLastError();
+  e = launch_loss(fit, prog, blocks, tiles, 0, mask_words, st);
   if (e != cudaSuccess) return e;
-  finish_lambda_kernel<<<1, kPassThreads, 0, st>>>(fit, prog, blocks, round_id);
+  finish_lambda_kernel<<<1, kPassThreads, 0, st>>>(fit, prog, tiles > 0 ? tiles : blocks, round_id);
   return cudaGetLastError();
 }
 
@@ -357,11 +584,10 @@ __global__ void store_epoch_loss_kernel(FitDev* __restrict__ fit, const Progress
   f.losses[size_t(pg.lambda_ind) * f.max_iter + (pg.it_outer - 1)] = loss;
 }
 
-cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, cudaStream_t st) {
-  loss_pass_kernel<<<blocks, kPassThreads, 0, st>>>(fit, prog, 1, 0);
-  cudaError_t e = cudaGetLastError();
+cudaError_t launch_epoch_loss(FitDev* fit, Progress* prog, int blocks, int tiles, cudaStream_t st) {
+  cudaError_t e = launch_loss(fit, prog, blocks, tiles, 1, 0, st);
   if (e != cudaSuccess) return e;
-  store_epoch_loss_kernel<<<1, 32, 0, st>>>(fit, prog, blocks);
+  store_epoch_loss_kernel<<<1, 32, 0, st>>>(fit, prog, tiles > 0 ? tiles : blocks);
   return cudaGetLastError();
 }
 

@@ -328,7 +328,9 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   auto fetch_y = [&](uint32_t sx) { return f.yt[size_t(sx) * Ky + (Ky == 1 ? 0 : lane)]; };
   uint32_t s_cur = 0, s_n1 = 0, s_n2 = 0;
   double y_cur = 0.0, gm_cur = 0.0;
-  uint32_t a_mine = 0, a_pbar = 0;      // this lane's slot in part[0][cta][] and pbar[0], as shared-window addresses
+  // exchange role of a control lane: class xk to destination CTA xd (+ 32 / KT per round)
+  const uint32_t xk = static_cast<uint32_t>(lane) % KT, xd = static_cast<uint32_t>(lane) / KT;
+  uint32_t a_mine = 0, a_pbar = 0;      // slot of class xk in part[0][cta][] and pbar[0], as shared-window addresses
   if (control) {
     s_cur = seq[0];
     s_n1 = (total > 1) ? seq[1] : 0u;
@@ -339,7 +341,7 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       y_cur = fetch_y(s_cur);
       if (cta == 0) gm_cur = f.gmem[size_t(s_cur) * K + lane];
     }
-    a_mine = smem_u32(&sm.part[0][cta][lane]);
+    a_mine = smem_u32(&sm.part[0][cta][xk]);
     a_pbar = smem_u32(&sm.pbar[0]);
   }
   constexpr uint32_t kParStride = (kCluster + 1) * 32 * 8;                 // bytes between the two parities of part[]
@@ -356,16 +358,21 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         double tsum = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tsum += sm.red[w][lane];
-        if (valid) {
+        // the K sums go to nct CTAs: (class, destination) pairs are spread over the 32 lanes, 32 / KT destinations per
+        // round, so the control warp issues one or two remote stores per lane instead of a chain of 2 * nct
+        {
+          constexpr uint32_t kDestPerRound = 32 / KT;
           const uint32_t a_sum = a_mine + xpar * kParStride, a_bar = a_pbar + xpar * 8u;
+          const double v_sum = __shfl_sync(kFull, tsum, xk);
+          const double v_gm = __shfl_sync(kFull, gm_cur, xk);
 #pragma unroll
-          for (uint32_t c = 0; c < kCluster; ++c)
-            if (c < nct) st_async_f64(map_to_cta(a_sum, c), tsum, map_to_cta(a_bar, c));
-          if (cta == 0) {
-            // part[xpar][kCluster][lane] (a_mine points into row cta == 0 here)
-#pragma unroll
-            for (uint32_t c = 0; c < kCluster; ++c)
-              if (c < nct) st_async_f64(map_to_cta(a_sum + kGmOffset, c), gm_cur, map_to_cta(a_bar, c));
+          for (uint32_t c0 = 0; c0 < kCluster; c0 += kDestPerRound) {
+            const uint32_t c = c0 + xd;
+            if (c0 < nct && c < nct && static_cast<int>(xk) < K) {
+              const uint32_t bar_c = map_to_cta(a_bar, c);
+              st_async_f64(map_to_cta(a_sum, c), v_sum, bar_c);
+              if (cta == 0) st_async_f64(map_to_cta(a_sum + kGmOffset, c), v_gm, bar_c);   // part[xpar][kCluster][k]
+            }
           }
         }
         // this CTA expects (nct + 1) * K doubles per update on its own barrier: one local arrival arms the phase
