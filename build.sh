@@ -14,5 +14,5 @@ for f in saga_dense saga_dense_cluster saga_dense_cluster_generic saga_sparse pa
   fi
 done
 for pid in $pids; do wait $pid || { echo "build.sh: a compile failed" >&2; exit 1; }; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libsgdnet_b200.so ../../build/saga_dense.o ../../build/saga_dense_cluster.o ../../build/saga_dense_cluster_generic.o ../../build/saga_sparse.o ../../build/passes.o ../../build/rng.o ../../build/setup.o ../../build/host_setup.o ../../build/engine.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libsgdnet_b200.so ../../build/saga_dense.o ../../build/saga_dense_cluster.o ../../build/saga_dense_cluster_generic.o ../../build/saga_sparse.o ../../build/passes.o ../../build/rng.o ../../build/setup.o ../../build/host_setup.o ../../build/engine.o -lcudart -ldl
 echo built sgdnet_b200/libsgdnet_b200.so

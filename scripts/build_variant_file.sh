@@ -12,5 +12,5 @@ OBJS=""
 for f in saga_dense saga_dense_cluster saga_dense_cluster_generic saga_sparse passes rng setup host_setup engine; do
   if [ $f = $FILE ]; then OBJS="$OBJS ../../build/${FILE}_$NAME.o"; else OBJS="$OBJS ../../build/$f.o"; fi
 done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libsgdnet_b200_$NAME.so $OBJS -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libsgdnet_b200_$NAME.so $OBJS -lcudart -ldl
 echo built $NAME

@@ -1,14 +1,20 @@
 // engine.cu — the extern "C" boundary (include/sgdnet_b200.h) and the lambda-path driver behind it.
 //
 // What replaces what: sgdnet_fit_dense / sgdnet_fit_sparse are SgdnetDense / SgdnetSparse (reference
-// src/sgdnet.cpp:359-375); the driver below is SetupSgdnet's lambda loop (src/sgdnet.cpp:217-273) turned into a
-// per-fit state machine that lives on the device (Progress): every "round" the host launches
-//     lag-scaling table (new lambda only) -> SAGA epochs -> [debug epoch loss] -> deviance + rescale + archive
-// once for ALL fits of a batch (one CTA per fit for the solver, grid-wide passes for the streaming kernels), then
-// reads the few bytes of Progress back. Warm-start state never leaves HBM (src/sgdnet.cpp:186-198).
-// The sampling sequence is produced on the host in the reference's order (floor(runif(0,n)) per update) and
-// uploaded ahead of the launch; draws that a converged epoch did not consume are kept for the next lambda, and the
-// generator handed back to the caller has advanced by exactly n * npasses draws.
+// src/sgdnet.cpp:359-375); sgdnet_fit_batch_* is the cv_sgdnet double loop (R/cv_sgdnet.R:160-200). The driver below
+// is SetupSgdnet's lambda loop (src/sgdnet.cpp:217-273) turned into a per-fit state machine that lives on the device
+// (Progress). Every fit of a batch is its own asynchronous pipeline on its own pair of streams:
+//     [sampling indices (rng.cu) -> conflict codes] -> lag-scaling table (new lambda only) -> SAGA epochs
+//     -> [debug epoch loss] -> deviance + rescale + archive (finish-lambda)
+// The kernel that ends a step publishes the fit's Progress to pinned host memory; one host thread polls the fits'
+// round ids and submits each fit's next launch as soon as its last one has published (no lock-step rounds, no stream
+// synchronisation, any mix of kernel variants in one batch). The next launch's indices and conflict codes are
+// prepared on the fit's second stream while the current launch solves. Warm-start state never leaves HBM
+// (src/sgdnet.cpp:186-198). The design-level setup (CSC -> CSR, column statistics, scaling, row subsets, largest row
+// norm, X^T y) runs on the device (setup.cu); the O(n) response statistics and the lambda grid stay on the host
+// (host_setup.cu). With R's default generator the sampling sequence is produced on the device and the caller's
+// generator is handed back advanced by exactly n * npasses draws; other generators (callback, fixed sequence) are
+// drawn on the host in the reference's order, one launch ahead.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -28,6 +34,8 @@
 
 #include "../../include/sgdnet_b200.h"
 #include "host_setup.h"
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.h"
 #include "setup.h"
 
@@ -217,6 +225,8 @@ struct FitJob {
   bool idx_on_prep = false;           // this launch's indices were produced on st_prep
   bool needs_finish = false;          // the last solver launch ended a lambda (or, debug mode, an epoch): passes are due
   bool stale_prep = false;            // a prepared launch was discarded; its kernels may still be running on st_prep
+  nvtxRangeId_t nvtx_launch = 0, nvtx_lambda = 0;      // open NVTX ranges (one per solver launch, one per lambda)
+  bool nvtx_lambda_open = false;
   int loss_blocks = 1;
   int loss_tiles = 0;                 // > 0: CTAs of the bulk-copy tile form of the loss pass (sparse K == 1)
   int mask_words = 0;                 // sparse K == 1: words of the nonzero-coefficient bitmap (0: p too large for it)
@@ -744,6 +754,17 @@ struct Engine {
     const int ne = ne_fixed > 0 ? ne_fixed
                                 : static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(epl), std::max<uint32_t>(left, 1u)));
     const int b = j.buf;
+    {      // NVTX: one range per lambda and one per solver launch of every fit (they overlap across fits: start/end ranges)
+      char name[96];
+      const int fit_no = static_cast<int>(&j - jobs.data());
+      if (!j.nvtx_lambda_open) {
+        std::snprintf(name, sizeof(name), "sgdnet fit %d lambda %d", fit_no, pg.lambda_ind);
+        j.nvtx_lambda = nvtxRangeStartA(name);
+        j.nvtx_lambda_open = true;
+      }
+      std::snprintf(name, sizeof(name), "sgdnet fit %d lambda %d launch %u (%d epochs)", fit_no, pg.lambda_ind, j.round_id + 1, ne);
+      j.nvtx_launch = nvtxRangeStartA(name);
+    }
     RoundArgs ra{j.seq_dev[b], j.dep_dev[b], j.dup_dev[b], ne, flags, ++j.round_id, 0u};
     const int64_t n = j.dev.n;
     if (j.prepped) {
@@ -813,6 +834,7 @@ struct Engine {
   }
 
   void solver_done(FitJob& j) {
+    nvtxRangeEnd(j.nvtx_launch);
     const Progress pg = *j.mirror;
     const uint64_t used_epochs = pg.epochs_last_launch;
     const uint64_t used = used_epochs * uint64_t(j.dev.n);
@@ -865,6 +887,10 @@ struct Engine {
     }
     j.seconds_dev += ms * 1e-3;
     j.needs_finish = false;
+    if (j.nvtx_lambda_open && j.mirror->status != kLambdaDone) {      // the lambda's deviance / archive pass is through
+      nvtxRangeEnd(j.nvtx_lambda);
+      j.nvtx_lambda_open = false;
+    }
   }
 
   bool use_events() const { return jobs.size() == 1; }

@@ -96,6 +96,8 @@ struct __align__(128) ClusterFixed {
   double gch[32];
   double conv[2][kCluster][2];        // epoch-end maxima from every CTA
   double cred[8][2];
+  double exp_tab[64];                 // sgd_exp's 2^(j/32) table (hi, lo): per-lane indices would serialise in the constant cache
+  double consts[2][4];                // step constants of the update (parity): gamma / wscale, step, threshold, wscale after the step
   uint64_t full[kCRing];
   uint64_t pbar[2];                   // partial sums arrived (count 1 + transaction bytes: (kCluster + 1) * K doubles per update)
   uint64_t cbar[2];                   // epoch-end maxima arrived (count 1 + transaction bytes)
@@ -156,13 +158,36 @@ __device__ __forceinline__ double sgd_log_sum(double x) {
   return out;
 }
 
+// sgd_exp_inrange (common.cuh) reading the 2^(j/32) table from shared memory: the same operations and bits
+__device__ __forceinline__ double sgd_exp_inrange_tab(double x, const double* __restrict__ tab) {
+  const double kInvStep = 46.16624130844683, kStepHi = 0.021660849392446835, kStepLo = 5.145609244655338e-14;
+  const double kShift = 6755399441055744.0;
+  const double ts = fma(x, kInvStep, kShift);
+  const double kd = ts - kShift;
+  const int32_t k = __double2loint(ts);
+  double r = fma(-kd, kStepHi, x);
+  r = fma(-kd, kStepLo, r);
+  double p = 1.0 / 720.0;
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  const double q = fma(r * r, p, r);
+  const int32_t j = k & 31, m = k >> 5;
+  const double2 t = *reinterpret_cast<const double2*>(tab + 2 * j);
+  const double res = t.x + fma(t.x, q, t.y);
+  const double out = res * __hiloint2double((m + 1023) << 20, 0);
+  if (__builtin_expect(!(x >= -707.0 && x <= 709.0), 0)) return sgd_exp_rare(x);
+  return out;
+}
+
 // LogSumExp (src/math.h:25-33) over the classes held one per lane (lanes that hold no class pass valid = false), the
 // bits of lse_warp (common.cuh), for at most KT classes in lanes 0 .. KT-1. The maximum is exact in any order: two
 // integer warp reductions over an order-preserving key replace five shuffle-and-compare rounds. The sum is the
 // 32-slot butterfly padded with zeros (include/sgdnet_arith.h, item 2): the levels whose partner lanes all hold the
 // pad (offsets >= KT) add +0.0 to a non-negative number and are skipped.
 template <int KT>
-__device__ __forceinline__ double lse_classes(double lp, bool valid, int lane) {
+__device__ __forceinline__ double lse_classes(double lp, bool valid, int lane, const double* __restrict__ exp_tab) {
   const long long b = __double_as_longlong(valid ? lp : -INFINITY);
   const unsigned long long key = b < 0 ? ~static_cast<unsigned long long>(b) : (static_cast<unsigned long long>(b) | 0x8000000000000000ull);
   const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
@@ -170,7 +195,7 @@ __device__ __forceinline__ double lse_classes(double lp, bool valid, int lane) {
   const unsigned lmax = __reduce_max_sync(kFull, hi == hmax ? lo : 0u);
   const unsigned long long kmax = (static_cast<unsigned long long>(hmax) << 32) | lmax;
   const double mx = __longlong_as_double((kmax >> 63) ? static_cast<long long>(kmax & 0x7fffffffffffffffull) : static_cast<long long>(~kmax));
-  double e = valid ? sgd_exp_inrange(lp - mx) : 0.0;
+  double e = valid ? sgd_exp_inrange_tab(lp - mx, exp_tab) : 0.0;
 #pragma unroll
   for (int o = (KT >= 32 ? 16 : KT / 2); o > 0; o >>= 1) e += __shfl_xor_sync(kFull, e, o);
   const double sum = (lane < KT) ? e : 1.0;      // lanes beyond the first group hold no class and no sum
@@ -258,6 +283,11 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   }
   for (int i = threadIdx.x; i < 2 * (kCluster + 1) * 32; i += kCBlock) (&sm.part[0][0][0])[i] = 0.0;
   for (int i = threadIdx.x; i < 8 * 32; i += kCBlock) (&sm.red[0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < 64; i += kCBlock) sm.exp_tab[i] = sgd_exp_tab_dev[i];
+  if (threadIdx.x == 0) {       // step constants of the first update (wscale == 1)
+    sm.consts[0][0] = gamma / (1.0 * r);
+    sm.consts[0][1] = bgs / (1.0 * r);
+  }
 
   // feature slot (i, tid)  <->  feature j = 2048 * i + 256 * cta + tid
   const int jbase = kCT * static_cast<int>(cta) + tid;
@@ -389,11 +419,11 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         double g;
         if (family == kMultinomial) {
           const double yc = __shfl_sync(kFull, y_cur, 0);
-          const double lse = lse_classes<KT>(lp, valid, lane);
-          g = sgd_exp_inrange(lp - lse);
+          const double lse = lse_classes<KT>(lp, valid, lane, sm.exp_tab);
+          g = sgd_exp_inrange_tab(lp - lse, sm.exp_tab);
           if (static_cast<unsigned>(lane) == static_cast<unsigned>(yc + 0.5)) g -= 1.0;
         } else if (family == kBinomial) {
-          g = 1.0 - y_cur - 1.0 / (1.0 + sgd_exp(lp));
+          g = 1.0 - y_cur - 1.0 / (1.0 + sgd_exp_inrange_tab(lp, sm.exp_tab));
         } else {
           g = lp - y_cur;
         }
@@ -412,6 +442,14 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         }
         if (wscale < kSmall) wscale = 1.0;
         wscale *= r;
+        {      // step constants of the next update (the coefficient scale is back at 1 when an epoch begins)
+          const double w_next = (t + 1 == n) ? 1.0 : wscale;
+          const double ws_n = ((w_next < kSmall) ? 1.0 : w_next) * r;
+          if (lane == 0) {
+            sm.consts[(tg + 1) & 1][0] = gamma / ws_n;
+            sm.consts[(tg + 1) & 1][1] = bgs / ws_n;
+          }
+        }
         if (issuer && tg + kCRing < total) {      // the slot this update's row sat in is free: every lane read it before barrier 1
           issue_row(tg + kCRing, s_refill);
           if (tg + kCRing + 1 < total) s_refill = seq[tg + kCRing + 1];
@@ -432,9 +470,8 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       // ================================================================ feature warps
       for (int64_t t = 0; t < n; ++t, ++tg) {
         const int slot = static_cast<int>(tg & (kCRing - 1));
-        const uint32_t parity = static_cast<uint32_t>((tg / kCRing) & 1);
         CLTRACE(4, fwarp == 0);
-        mbar_wait(&sm.full[slot], parity);
+        if (tg == 0) mbar_wait(&sm.full[0], 0u);      // later rows are waited for in the shadow of the previous exchange
         CLTRACE(5, fwarp == 0);
         // ---- A: partial dot products of this lane (ascending j), warp butterfly by recursive halving, warp sums
         double x[NCH];
@@ -456,16 +493,18 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         if ((lane & ((1 << kShift) - 1)) == 0) sm.red[fwarp][lane >> kShift] = tot;
         CLTRACE(6, fwarp == 0);
         bar_arrive_named(1);
-        // this update's step constants (functions of the deterministic wscale track), while the control warp exchanges:
-        // gamma / wscale, (beta gamma) / wscale with wscale as it will be after this step
+        // this update's step constants are functions of the deterministic wscale track: the two divisions (gamma / wscale,
+        // (beta gamma) / wscale with wscale as it will be after this step) were done by the control warp in its slack
         const bool reset = wscale < kSmall;
         const double ws_c = (reset ? 1.0 : wscale) * r;
-        const double gw = gamma / ws_c;
-        const double step = gamma / ws_c * 1.0;
-        const double thr = bgs / ws_c;
-        CLTRACE(7, fwarp == 0 && thr != 12345.678);
+        // the next update's row (its copy was issued kCRing - 1 updates ago): a completed mbarrier still costs a probe
+        // of about 90 cycles, spent here while the control warp exchanges instead of at the head of the next update
+        if (tg + 1 < total) mbar_wait(&sm.full[(tg + 1) & (kCRing - 1)], static_cast<uint32_t>(((tg + 1) / kCRing) & 1));
         bar_sync_named(2);                                                  // g_change is in gch[]
         CLTRACE(8, fwarp == 0);
+        const double gw = sm.consts[tg & 1][0];
+        const double step = gw * 1.0;
+        const double thr = sm.consts[tg & 1][1];
         double gch[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) gch[k] = sm.gch[k];

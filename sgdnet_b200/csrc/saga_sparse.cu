@@ -113,7 +113,7 @@ __device__ __forceinline__ bool block_converged(double mc, double ms, double* re
 //  - a row whose nonzeros do not fit a ring slot, or at which the wscale reset (src/saga-sparse.h:285-295) fires,
 //    is run serially: it waits for every earlier row, and the rows after it wait for it.
 constexpr int kWSlots = 32;     // row ring depth: S rows held by the workers + rows in flight from HBM
-constexpr int kSeq = 32;        // per-row barrier / queue rings (indexed by row sequence number)
+constexpr int kSeq = 16;        // per-row barrier / queue / forwarding rings (indexed by row sequence number; at most S <= 12 rows are in flight)
 static_assert(kChunks == 4, "conflict codes pack four 16-bit entries per lane");
 
 struct WaveSlotMeta {
@@ -182,7 +182,7 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 // ran serially). Lane l of a worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
 constexpr uint32_t kCodeGlobal = 1u << 11;
 
-constexpr int kDepRows = 32;      // row instances per block iteration (4 per warp)
+constexpr int kDepRows = 24;      // row instances per block iteration (3 per warp; 48 KB of shared memory: two CTAs fit beside a solver CTA)
 constexpr int kDepMaxWindow = 15;  // distances are 4-bit
 constexpr int kDepBitWords = 256;  // 8192-bit filter per row, two hash functions: ~0.06 % false positives at 100 entries
 __device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 19; }   // 13 bits
