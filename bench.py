@@ -17,7 +17,7 @@ libsgdnet_b200.so.
   cv           BASELINE metric (iii) / config 5 at FULL spec: 10-fold x 5-alpha cv_sgdnet, binomial sparse 500k x 50k,
                100 lambdas, thresh 1e-3 - all 55 fits dealt to the N ranks, one NCCL all_gather of the score rows
   dense        configs 3 and 4 (dense multinomial 60000 x 784 K=10; dense mgaussian 200000 x 2000 K=4): updates/s of
-               saga_dense_kernel at full size
+               saga_dense_cluster_kernel at full size
   cpu_baseline the reference's CPU path (oracle/_ref and the restated oracle, the faster of the two; g++ -O2, 1 thread:
                the reference is single-threaded) on a bounded sample of the same workload, timed on this box
 
@@ -293,7 +293,8 @@ def part_cv(lib, args, shard, dist, world):
 
 
 def part_dense(lib):
-    """Configs 3 and 4 at full size: saga_dense_kernel epochs through the stepping interface (design resident)."""
+    """Configs 3 and 4 at full size: epochs of the dense cluster kernel (saga_dense_cluster.cu; p >= 512) through the stepping
+    interface (design resident)."""
     from sgdnet_b200 import _abi, api, synth
     out = {}
     for name, gen, fam, K, alpha, epochs in (("config3_multinomial_60000x784_K10", lambda: synth.multinomial_dense(60_000, 784, 10, seed=1003), "multinomial", 10, 0.8, 3),
@@ -318,7 +319,8 @@ def part_dense(lib):
         t = min(times[1:]) * 1e-3
         b_upd = 8 * p + 4 + 8 * (K if fam == "mgaussian" else 1) + 16 * K
         out[name] = {"updates_per_s": n / t, "epoch_ms": t * 1e3, "bytes_per_update": b_upd, "algorithmic_GBps": n / t * b_upd / 1e9,
-                     "kernel": "saga_dense_kernel"}
+                     "kernel": "saga_dense_cluster_kernel (thread-block cluster, one per fit)",
+                     "cycles_per_update_at_1965MHz": t / n * 1.965e9}
         del x, xa
     return out
 

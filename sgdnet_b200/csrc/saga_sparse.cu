@@ -182,107 +182,151 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 // ran serially). Lane l of a worker reads one 64-bit word holding the entries of positions l, l+32, l+64, l+96.
 constexpr uint32_t kCodeGlobal = 1u << 11;
 
-constexpr int kDepRows = 24;      // row instances per block iteration (3 per warp; 48 KB of shared memory: two CTAs fit beside a solver CTA)
-constexpr int kDepMaxWindow = 15;  // distances are 4-bit
-constexpr int kDepBitWords = 256;  // 8192-bit filter per row, two hash functions: ~0.06 % false positives at 100 entries
+constexpr int kDepSlots = 32;       // row instances staged per block iteration: the `window` rows before the block's rows + its own
+constexpr int kDepMaxWindow = 15;   // distances are 4-bit
+constexpr int kDepBuckets = 8192;   // hashed feature buckets; a bucket holds one bit per staged row
 __device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 19; }   // 13 bits
 __device__ __forceinline__ uint32_t dep_hash2(int32_t j) { return (static_cast<uint32_t>(j) * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
 
-__global__ void __launch_bounds__(256)
+// Which features of a row are also held by one of the `window` rows before it. Per block iteration 32 consecutive row
+// instances (the last 32 - window of them are the block's own) are staged in shared memory: their index runs, and ONE
+// table of 8192 hashed feature buckets x 32 bits - bit r of bucket h says "staged row r holds a feature that hashes to
+// h" (two hash functions into the same table). A feature of row r is then tested against ALL its predecessors with two
+// loads: table[h1] & table[h2], masked to the rows of its window, is the set of rows that MAY hold it (each wrongly
+// with probability (200 / 8192)^2 = 0.06 %); the candidates, nearest first, are confirmed by binary search in their
+// sorted index runs, which also yields the feature's position there. This is exact, and a quarter of the shared-memory
+// traffic of testing seven per-row filters one after the other (the first form of this kernel): the pass costs the
+// many-fits regime as much SM time as it saves the solver, so its cost per row is what bounds a batch.
+constexpr int kDepWarps = 8;
+constexpr int kDepPerWarp = kDepSlots / kDepWarps;      // staged rows per warp and block iteration
+__global__ void __launch_bounds__(kDepWarps * 32, 4)
 wave_deps_kernel(const FitDev* __restrict__ fit, const RoundArgs ra, int window) {
-  // the index runs of the block's rows and of the `window` rows before them, staged once in shared memory: the
-  // membership searches below then never leave the SM
   extern __shared__ __align__(16) unsigned char deps_smem[];
-  const int nslots_alloc = kDepRows + window;
   int32_t (*sidx)[kCap] = reinterpret_cast<int32_t (*)[kCap]>(deps_smem);
-  uint32_t (*sbits)[kDepBitWords] = reinterpret_cast<uint32_t (*)[kDepBitWords]>(deps_smem + size_t(nslots_alloc) * kCap * 4);   // hashed membership filter per row
-  int32_t* snnz = reinterpret_cast<int32_t*>(deps_smem + size_t(nslots_alloc) * (kCap + kDepBitWords) * 4);
-  uint32_t* ssamp = reinterpret_cast<uint32_t*>(snnz + nslots_alloc);
+  uint32_t* table = reinterpret_cast<uint32_t*>(deps_smem + sizeof(int32_t) * kDepSlots * kCap);
+  int32_t* snnz = reinterpret_cast<int32_t*>(table + kDepBuckets);
+  uint32_t* ssamp = reinterpret_cast<uint32_t*>(snnz + kDepSlots);
+  uint32_t& slong = *(ssamp + kDepSlots);   // staged rows too long for a ring slot (they run serially; their features come from HBM)
   // depends on the sampling sequence alone (not on the fit's progress), so it can run ahead of the solver
   if (ra.n_epochs <= 0 || ra.dep == nullptr) return;
   const FitDev& f = *fit;
   const int64_t n = f.n;
   const int64_t total = n * ra.n_epochs;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t* __restrict__ ci = f.ci;
-  const int nslots = kDepRows + window;
-  const int64_t n_chunks = (total + kDepRows - 1) / kDepRows;
+  const int own = kDepSlots - window;                 // rows of its own per block iteration
+  const int64_t n_chunks = (total + own - 1) / own;
+
+  // Staging is a chain of three dependent global loads (sequence -> row descriptor -> index run). It is software-
+  // pipelined over the block iterations so that no warp ever waits for it: while iteration i is searched, the index
+  // runs of iteration i + 1 and the descriptors of iteration i + 2 are in flight. Warp w stages slots w, w + 8, ...
+  uint32_t s_a[kDepPerWarp], s_b[kDepPerWarp];          // samples of the next / the one after next iteration's slots
+  RowInfo ri_a[kDepPerWarp], ri_b[kDepPerWarp];
+  int32_t jj[kDepPerWarp][kChunks];                     // index values of the next iteration's slots (lane e, e + 32, ...)
+  auto fetch_desc = [&](int64_t chunk, uint32_t (&sv)[kDepPerWarp], RowInfo (&rv)[kDepPerWarp]) {
+#pragma unroll
+    for (int u = 0; u < kDepPerWarp; ++u) {
+      const int64_t q = chunk * own - window + (warp + kDepWarps * u);
+      sv[u] = 0xffffffffu;
+      rv[u] = RowInfo{};
+      if (chunk < n_chunks && q >= 0 && q < total) {
+        sv[u] = ra.seq[q];
+        rv[u] = f.rows[sv[u]];
+      }
+    }
+  };
+  auto fetch_idx = [&](const RowInfo (&rv)[kDepPerWarp]) {
+#pragma unroll
+    for (int u = 0; u < kDepPerWarp; ++u)
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int e = c * 32 + lane;
+        jj[u][c] = (rv[u].nnz <= kCap && e < rv[u].nnz) ? ci[rv[u].start + e] : -1;
+      }
+  };
+  fetch_desc(blockIdx.x, s_a, ri_a);
+  fetch_idx(ri_a);
+  fetch_desc(int64_t(blockIdx.x) + gridDim.x, s_b, ri_b);
+
   for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int64_t q0 = chunk * kDepRows;
+    const int64_t q0 = chunk * own;
     __syncthreads();                                   // the previous iteration's searches are done
-    for (int r = warp; r < nslots; r += nwarps) {      // slot r holds row instance q0 - window + r
-      const int64_t q = q0 - window + r;
-      int32_t nnz = 0;
-      uint32_t s = 0xffffffffu;
+    for (int i = threadIdx.x; i < kDepBuckets; i += blockDim.x) table[i] = 0u;
+    if (threadIdx.x == 0) slong = 0u;
+    __syncthreads();
+    // ---- this iteration's rows from the registers into shared memory
 #pragma unroll
-      for (int wd = 0; wd < kDepBitWords / 32; ++wd) sbits[r][lane + 32 * wd] = 0u;
-      __syncwarp();
-      if (q >= 0 && q < total) {
-        s = ra.seq[q];
-        const RowInfo ri = f.rows[s];
-        nnz = ri.nnz;
-        if (nnz <= kCap) {
+    for (int u = 0; u < kDepPerWarp; ++u) {
+      const int r = warp + kDepWarps * u;              // slot r holds row instance q0 - window + r
+      const int32_t nnz = ri_a[u].nnz;
+      if (nnz <= kCap) {
+        const uint32_t bit = 1u << r;
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            const int e = c * 32 + lane;
-            if (e < nnz) {
-              const int32_t jj = ci[ri.start + e];
-              sidx[r][e] = jj;
-              const uint32_t h1 = dep_hash1(jj), h2 = dep_hash2(jj);
-              atomicOr(&sbits[r][h1 >> 5], 1u << (h1 & 31u));
-              atomicOr(&sbits[r][h2 >> 5], 1u << (h2 & 31u));
-            }
+        for (int c = 0; c < kChunks; ++c) {
+          const int32_t j = jj[u][c];
+          if (j >= 0) {
+            sidx[r][c * 32 + lane] = j;
+            atomicOr(&table[dep_hash1(j)], bit);
+            atomicOr(&table[dep_hash2(j)], bit);
           }
         }
+      } else if (lane == 0) {
+        atomicOr(&slong, 1u << r);
       }
       if (lane == 0) {
         snnz[r] = nnz;
-        ssamp[r] = s;
+        ssamp[r] = s_a[u];
       }
     }
+    // ---- next iteration's index runs (their descriptors arrived an iteration ago) and the descriptors after them
+#pragma unroll
+    for (int u = 0; u < kDepPerWarp; ++u) {
+      s_a[u] = s_b[u];
+      ri_a[u] = ri_b[u];
+    }
+    fetch_idx(ri_a);
+    fetch_desc(chunk + 2 * int64_t(gridDim.x), s_b, ri_b);
     __syncthreads();
-    for (int rl = warp; rl < kDepRows; rl += nwarps) {
+    const uint32_t long_rows = slong;
+    for (int rl = warp; rl < own; rl += kDepWarps) {
       const int64_t q = q0 + rl;
       if (q >= total) break;
       const int64_t t = q % n;
       const int me = window + rl;
       const int32_t nnz = snnz[me];
-      const uint32_t s = ssamp[me];
-      int j[kChunks];
-      uint32_t ent[kChunks], hw[kChunks], hb[kChunks], hw2[kChunks], hb2[kChunks];
+      const int dmax = static_cast<int>(t < window ? t : window);      // only rows of the same epoch
+      // staged rows me - dmax .. me - 1
+      const uint32_t wmask = ((1u << me) - 1u) & ~((1u << (me - dmax)) - 1u);
+      // nearest predecessor with the same sample: lane d - 1 looks at distance d
+      const uint32_t same = __ballot_sync(0xffffffffu, lane < dmax && ssamp[me - 1 - (lane < dmax ? lane : 0)] == ssamp[me]);
+      const uint32_t dupd = same ? static_cast<uint32_t>(__ffs(same)) : 0u;
+      uint32_t ent[kChunks];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int e = c * 32 + lane;
-        j[c] = (nnz <= kCap && e < nnz) ? sidx[me][e] : -1;
         ent[c] = 0;
-        const uint32_t h1 = dep_hash1(j[c]), h2 = dep_hash2(j[c]);
-        hw[c] = h1 >> 5;
-        hb[c] = 1u << (h1 & 31u);
-        hw2[c] = h2 >> 5;
-        hb2[c] = 1u << (h2 & 31u);
-      }
-      uint32_t dupd = 0;
-      const int dmax = static_cast<int>(t < window ? t : window);
-      for (int d = 1; d <= dmax; ++d) {
-        const int pr = me - d;
-        if (ssamp[pr] == s && dupd == 0) dupd = static_cast<uint32_t>(d);
-        const int32_t nnz2 = snnz[pr];
-        if (nnz2 == 0) continue;
-        const int32_t* __restrict__ c2 = sidx[pr];
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          if (j[c] < 0 || ent[c] != 0) continue;
-          if (nnz2 > kCap) {
-            ent[c] = static_cast<uint32_t>(d) | kCodeGlobal;
-            continue;
+        if (nnz > kCap || e >= nnz) continue;
+        const int32_t j = sidx[me][e];
+        uint32_t cand = ((table[dep_hash1(j)] & table[dep_hash2(j)]) | long_rows) & wmask;
+        while (cand != 0u) {                            // nearest predecessor first
+          const int pr = 31 - __clz(cand);
+          cand &= ~(1u << pr);
+          const uint32_t d = static_cast<uint32_t>(me - pr);
+          if ((long_rows >> pr) & 1u) {
+            ent[c] = d | kCodeGlobal;
+            break;
           }
-          if ((sbits[pr][hw[c]] & hb[c]) == 0u || (sbits[pr][hw2[c]] & hb2[c]) == 0u) continue;   // certainly absent
-          int lo = 0, hi = nnz2;               // first position with c2[pos] >= j[c]
+          const int32_t nnz2 = snnz[pr];
+          const int32_t* __restrict__ c2 = sidx[pr];
+          int lo = 0, hi = nnz2;                        // first position with c2[pos] >= j
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (c2[mid] < j[c]) lo = mid + 1; else hi = mid;
+            if (c2[mid] < j) lo = mid + 1; else hi = mid;
           }
-          if (lo < nnz2 && c2[lo] == j[c]) ent[c] = static_cast<uint32_t>(d) | (static_cast<uint32_t>(lo) << 4);
+          if (lo < nnz2 && c2[lo] == j) {
+            ent[c] = d | (static_cast<uint32_t>(lo) << 4);
+            break;
+          }
         }
       }
       // most rows share nothing with their window (82 % at config 2's density): their 256 B of codes are neither
@@ -1239,13 +1283,14 @@ static cudaError_t launch_wave(FitDev* fit, Progress* prog, const RoundArgs& ra,
 
 // `ctas`: how many CTAs this fit's conflict-code pass may use (the caller shares the GPU among the fits in flight)
 cudaError_t launch_wave_deps(const FitDev* fit, const RoundArgs& ra, int64_t rows, int ctas, cudaStream_t st) {
-  const int64_t want = (rows + kDepRows - 1) / kDepRows;
-  dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, ctas))));
   const int window = wave_warps() - 1;
-  const size_t smem = size_t(kDepRows + window) * ((kCap + kDepBitWords) * 4 + 8);
-  cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int own = kDepSlots - window;
+  const int64_t want = (rows + own - 1) / own;
+  dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, ctas))));
+  const size_t smem = sizeof(int32_t) * kDepSlots * kCap + sizeof(uint32_t) * (kDepBuckets + 2 * kDepSlots + 4);   // 48.3 KB
+  cudaError_t e = cudaFuncSetAttribute(wave_deps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (e != cudaSuccess) return e;
-  wave_deps_kernel<<<grid, 256, smem, st>>>(fit, ra, window);
+  wave_deps_kernel<<<grid, kDepWarps * 32, smem, st>>>(fit, ra, window);
   return cudaGetLastError();
 }
 
