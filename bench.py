@@ -480,7 +480,10 @@ def main():
 
     roofline_passes = None
     if "passes" not in args.skip and world == 1:
-        roofline_passes = part_passes(lib, sess, n, int(m.p[-1]), peak, rng)
+        try:
+            roofline_passes = part_passes(lib, sess, n, int(m.p[-1]), peak, rng)
+        except Exception as exc:      # noqa: BLE001
+            roofline_passes = {"error": f"{type(exc).__name__}: {exc}"}
     lib.sym("session_destroy")(sess)
 
     # ---------------- e2e: sgdnet_fit_sparse with host buffers
@@ -513,13 +516,19 @@ def main():
     del x, m
 
     # ---------------- many fits on one GPU; dense configs (N = 1 only)
-    batch = part_batch(lib, args) if ("batch" not in args.skip and world == 1) else None
-    dense = part_dense(lib) if ("dense" not in args.skip and world == 1) else None
+    def guarded(part, *a):      # a failing side measurement must not cost the run its headline line
+        try:
+            return part(*a)
+        except Exception as exc:      # noqa: BLE001
+            return {"error": f"{type(exc).__name__}: {exc}"}
+    batch = guarded(part_batch, lib, args) if ("batch" not in args.skip and world == 1) else None
+    dense = guarded(part_dense, lib) if ("dense" not in args.skip and world == 1) else None
 
     # ---------------- config 5 (cv): sharded over the run's ranks
     cv = None
     if "cv" not in args.skip:
-        cv = part_cv(lib, args, Shard.from_torch() if world > 1 else None, dist, world)
+        cv = part_cv(lib, args, Shard.from_torch() if world > 1 else None, dist, world) if world > 1 else guarded(
+            part_cv, lib, args, None, dist, world)
 
     # ---------------- cpu baseline (rank 0, N = 1 only)
     cpu = None
@@ -537,7 +546,7 @@ def main():
         cpu = {"value": best[0], "unit": "updates/s", "cores": 1, "kind": best[1],
                "sample": f"epochs 2-3 of a 3-epoch fit of n={n_cpu} rows (same generator, p={args.p}, {NNZ_ROW} nnz/row) at lambda[{args.lambda_ind}]; "
                          + best[2], "arms_timed": tried, "host_cores_available": os.cpu_count()}
-        if cv is not None:
+        if cv is not None and "error" not in cv:
             legs = part_cpu_cv(args)
             rate_p = legs["updates_per_s_per_core_with_all_workers_busy"]
             legs["sequential_s_extrapolated"] = cv["updates"] / legs["updates_per_s_one_core_alone"]

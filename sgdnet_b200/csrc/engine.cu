@@ -268,13 +268,13 @@ struct Engine {
   double* yraw_dev = nullptr;
   std::map<const int32_t*, int32_t*> test_dev;
 
+  int dev_id = 0;        // the device this engine lives on: helper threads must select it (a new host thread starts on device 0)
   Engine() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) throw CudaFail{e == cudaSuccess ? cudaErrorNoDevice : e, "no CUDA device (no CPU fallback)"};
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     arena.stream = stream;
-    int dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     // L2 persistence for the sparse coefficient records: measured on config 2, it changes neither the solver's time
@@ -593,7 +593,7 @@ struct Engine {
     f.nz_mask = job.mask_words ? arena.alloc<uint32_t>(mask_words) : nullptr;
     job.dense_cluster = job.variant == Variant::Dense && p >= SGD_WIDE_P;
     if (job.dense_cluster) {
-      job.dense_smem = dense_cluster_smem_bytes(K, p);
+      job.dense_smem = dense_cluster_smem_bytes(K, p, f.penalty);
       if (job.dense_smem > dense_smem_budget())
         throw std::invalid_argument("dense x with p = " + std::to_string(p) + " columns: the row ring of one cluster CTA exceeds its shared memory");
     } else if (job.variant == Variant::Dense) {
@@ -1295,10 +1295,15 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
         if (wave[i] == w) todo.push_back(i);
       std::atomic<size_t> next{0};
       auto work = [&]() {
+        const bool on_device = cudaSetDevice(eng.dev_id) == cudaSuccess;
         for (;;) {
           const size_t q = next.fetch_add(1);
           if (q >= todo.size()) break;
           const int i = todo[q];
+          if (!on_device) {
+            errs[i] = "cudaSetDevice failed in a planning thread";
+            continue;
+          }
           sgdnet_control ctl = specs[i].control;
           if (specs[i].lambda_from >= 0) {
             const std::vector<double>& lam = eng.jobs[specs[i].lambda_from].plan.lambda;
@@ -1308,6 +1313,8 @@ int fit_batch(const XArg& xa, const double* y, int32_t y_cols, sgdnet_fit_spec* 
           }
           try {
             errs[i] = eng.build_plan(eng.jobs[i], specs[i].train_rows, ctl);
+          } catch (const CudaFail& cf) {
+            errs[i] = std::string(cf.what) + ": " + cudaGetErrorString(cf.e);
           } catch (const std::exception& e) {
             errs[i] = e.what();
           }

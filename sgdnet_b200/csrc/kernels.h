@@ -29,7 +29,7 @@ int dense_kt_bucket(int K);
 // 1, 4, 8, 16 or 32: the class-count bucket a fit's kernel instantiation is compiled for
 // designs with p >= SGD_WIDE_P: one thread-block cluster of 8 CTAs per fit (saga_dense_cluster.cu; shapes without a
 // compile-time instantiation there go to saga_dense_cluster_generic.cu)
-size_t dense_cluster_smem_bytes(int K, int p);
+size_t dense_cluster_smem_bytes(int K, int p, int pen);
 cudaError_t launch_saga_dense_cluster(int K, int p, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 

@@ -227,17 +227,27 @@ namespace sgd {
 
 namespace {
 
-// KT: class-count bucket (1, 4, 8, 16, 32); PEN: penalty functor; NCH: 256-feature slices per CTA and row (1, 2, 4).
-template <int KT, int PEN, int NCH>
+// KT: class-count bucket (1, 4, 8, 16, 32); PEN: penalty functor; NCH: 256-feature slices per CTA and row (1, 2, 4);
+// CS: class split (1, 2, 4) - a design with at most 8 / CS feature blocks (p <= 2048 / CS) leaves CTAs of the cluster
+// without features, so the classes of a feature block are split over CS CTAs instead: CTA c owns feature block c % nfb
+// and the KT / CS classes from (c / nfb) * KT / CS on, which divides the feature warps' work per update (dot products,
+// butterfly, coefficient step) by CS. Per class the dot product's association does not change: its 256-lane block sums
+// still come one from each feature block. Not for the group lasso, whose prox couples the classes of a feature.
+template <int KT, int PEN, int NCH, int CS>
 __global__ void __launch_bounds__(kCBlock, 1)
 saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog, const RoundArgs ra) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr bool kReg = cluster_reg_state(KT, NCH);
+  constexpr int KL = KT / CS;                              // classes owned by this CTA's feature lanes
+  static_assert(CS == 1 || (NCH == 1 && PEN != kGroupLasso && KL >= 1), "class split: one slice, separable prox");
+  constexpr bool kReg = cluster_reg_state(KL, NCH);
   constexpr int kNF = NCH * kCT;
   Progress& pg = *prog;
   const FitDev& f = *fit;
   const uint32_t cta = cluster_ctarank();
-  const uint32_t nct = cluster_nctarank();     // 2, 4 or 8 CTAs: as many 256-feature blocks as the design has (at most 8)
+  const uint32_t nct = cluster_nctarank();     // 2, 4 or 8 CTAs: feature blocks of the design (at most 8) x class split
+  const uint32_t nfb = nct / CS;               // 256-feature blocks
+  const uint32_t fb = cta % nfb;               // this CTA's feature block ...
+  const int kbase = static_cast<int>(cta / nfb) * KL;      // ... and first class
   if (ra.n_epochs <= 0 || pg.status != kRunning) {       // uniform over the cluster
     if (cta == 0 && threadIdx.x == 0) {
       pg.epochs_last_launch = 0;
@@ -249,8 +259,8 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   const uint64_t t_start = globaltimer_ns();
 
   ClusterFixed<NCH>& sm = *reinterpret_cast<ClusterFixed<NCH>*>(smem_raw);
-  double* const Ws = reinterpret_cast<double*>(smem_raw + sizeof(ClusterFixed<NCH>));   // [KT][NCH * 256] when !kReg
-  double* const Gs = Ws + (kReg ? 0 : KT * kNF);
+  double* const Ws = reinterpret_cast<double*>(smem_raw + sizeof(ClusterFixed<NCH>));   // [KL][NCH * 256] when !kReg
+  double* const Gs = Ws + (kReg ? 0 : KL * kNF);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool control = warp == 0;
@@ -290,20 +300,20 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   }
 
   // feature slot (i, tid)  <->  feature j = 2048 * i + 256 * cta + tid
-  const int jbase = kCT * static_cast<int>(cta) + tid;
-  double Wr[kReg ? NCH * KT : 1], Gr[kReg ? NCH * KT : 1];
+  const int jbase = kCT * static_cast<int>(fb) + tid;
+  double Wr[kReg ? NCH * KL : 1], Gr[kReg ? NCH * KL : 1];
   if (!control) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int j = kLanes * i + jbase;
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        const bool have = j < p && k < K;
-        const double w0 = have ? Wg[size_t(k) * p + j] : 0.0;
-        const double g0 = have ? Gg[size_t(k) * p + j] : 0.0;
+      for (int k = 0; k < KL; ++k) {
+        const bool have = j < p && kbase + k < K;
+        const double w0 = have ? Wg[size_t(kbase + k) * p + j] : 0.0;
+        const double g0 = have ? Gg[size_t(kbase + k) * p + j] : 0.0;
         if constexpr (kReg) {
-          Wr[i * KT + k] = w0;
-          Gr[i * KT + k] = g0;
+          Wr[i * KL + k] = w0;
+          Gr[i * KL + k] = g0;
         } else {
           Ws[(k * NCH + i) * kCT + tid] = w0;
           Gs[(k * NCH + i) * kCT + tid] = g0;
@@ -326,14 +336,14 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   uint32_t row_bytes = 0;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int j0 = kLanes * i + kCT * static_cast<int>(cta);
+    const int j0 = kLanes * i + kCT * static_cast<int>(fb);
     const int len = (j0 >= ld) ? 0 : ((ld - j0 < kCT) ? ld - j0 : kCT);
     slice_b[i] = static_cast<uint32_t>(len) * 8u;
     row_bytes += slice_b[i];
   }
   auto issue_row = [&](int64_t q, uint32_t sq) {      // one thread; sq = seq[q]
     const int slot = static_cast<int>(q & (kCRing - 1));
-    const double* src = f.xd + size_t(sq) * ld + kCT * cta;
+    const double* src = f.xd + size_t(sq) * ld + kCT * fb;
     if (row_bytes == 0) {
       mbar_arrive(&sm.full[slot]);
       return;
@@ -358,8 +368,11 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   auto fetch_y = [&](uint32_t sx) { return f.yt[size_t(sx) * Ky + (Ky == 1 ? 0 : lane)]; };
   uint32_t s_cur = 0, s_n1 = 0, s_n2 = 0;
   double y_cur = 0.0, gm_cur = 0.0;
-  // exchange role of a control lane: class xk to destination CTA xd (+ 32 / KT per round)
-  const uint32_t xk = static_cast<uint32_t>(lane) % KT, xd = static_cast<uint32_t>(lane) / KT;
+  // exchange role of a control lane: local class xk to destination CTA xd (+ 32 / KL per round); CTA 0 sends the
+  // gradient memory of all classes the same way (class gk, destination gd + 32 / KT per round)
+  const uint32_t xk = static_cast<uint32_t>(lane) % KL, xd = static_cast<uint32_t>(lane) / KL;
+  const uint32_t gk = static_cast<uint32_t>(lane) % KT, gd = static_cast<uint32_t>(lane) / KT;
+  uint32_t a_gm = 0;
   uint32_t a_mine = 0, a_pbar = 0;      // slot of class xk in part[0][cta][] and pbar[0], as shared-window addresses
   if (control) {
     s_cur = seq[0];
@@ -371,7 +384,8 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       y_cur = fetch_y(s_cur);
       if (cta == 0) gm_cur = f.gmem[size_t(s_cur) * K + lane];
     }
-    a_mine = smem_u32(&sm.part[0][cta][xk]);
+    a_mine = smem_u32(&sm.part[0][fb][kbase + xk]);
+    a_gm = smem_u32(&sm.part[0][kCluster][gk]);
     a_pbar = smem_u32(&sm.pbar[0]);
   }
   constexpr uint32_t kParStride = (kCluster + 1) * 32 * 8;                 // bytes between the two parities of part[]
@@ -388,32 +402,39 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         double tsum = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tsum += sm.red[w][lane];
-        // the K sums go to nct CTAs: (class, destination) pairs are spread over the 32 lanes, 32 / KT destinations per
-        // round, so the control warp issues one or two remote stores per lane instead of a chain of 2 * nct
+        // this CTA's sums (its classes, its feature block) go to all nct CTAs: (class, destination) pairs are spread
+        // over the 32 lanes, 32 / KL destinations per round, so the control warp issues one or two remote stores per
+        // lane instead of a chain of them
         {
-          constexpr uint32_t kDestPerRound = 32 / KT;
+          constexpr uint32_t kDestPerRound = 32 / KL;
           const uint32_t a_sum = a_mine + xpar * kParStride, a_bar = a_pbar + xpar * 8u;
           const double v_sum = __shfl_sync(kFull, tsum, xk);
-          const double v_gm = __shfl_sync(kFull, gm_cur, xk);
 #pragma unroll
           for (uint32_t c0 = 0; c0 < kCluster; c0 += kDestPerRound) {
             const uint32_t c = c0 + xd;
-            if (c0 < nct && c < nct && static_cast<int>(xk) < K) {
-              const uint32_t bar_c = map_to_cta(a_bar, c);
-              st_async_f64(map_to_cta(a_sum, c), v_sum, bar_c);
-              if (cta == 0) st_async_f64(map_to_cta(a_sum + kGmOffset, c), v_gm, bar_c);   // part[xpar][kCluster][k]
+            if (c0 < nct && c < nct && kbase + static_cast<int>(xk) < K) st_async_f64(map_to_cta(a_sum, c), v_sum, map_to_cta(a_bar, c));
+          }
+          if (cta == 0) {
+            constexpr uint32_t kGmPerRound = 32 / KT;
+            const double v_gm = __shfl_sync(kFull, gm_cur, gk);
+#pragma unroll
+            for (uint32_t c0 = 0; c0 < kCluster; c0 += kGmPerRound) {
+              const uint32_t c = c0 + gd;
+              if (c0 < nct && c < nct && static_cast<int>(gk) < K)
+                st_async_f64(map_to_cta(a_gm + xpar * kParStride, c), v_gm, map_to_cta(a_bar, c));
             }
           }
         }
-        // this CTA expects (nct + 1) * K doubles per update on its own barrier: one local arrival arms the phase
-        if (lane == 0) mbar_expect_tx(&sm.pbar[xpar], (nct + 1u) * static_cast<uint32_t>(K) * 8u);
+        // this CTA expects (nfb + 1) * K doubles per update on its own barrier (per class one sum from every feature block,
+        // and the gradient memory): one local arrival arms the phase
+        if (lane == 0) mbar_expect_tx(&sm.pbar[xpar], (nfb + 1u) * static_cast<uint32_t>(K) * 8u);
         CLTRACE(1, true);
         mbar_wait(&sm.pbar[xpar], xphase);
         CLTRACE(2, true);
         double dot = 0.0;
 #pragma unroll
         for (int c = 0; c < kCluster; ++c)
-          if (c < static_cast<int>(nct)) dot += sm.part[xpar][c][lane];       // blocks beyond the design's features are exact zeros
+          if (c < static_cast<int>(nfb)) dot += sm.part[xpar][c][lane];       // blocks beyond the design's features are exact zeros
         const double gm_val = sm.part[xpar][kCluster][lane];
         const double lp = dot * wscale + b_reg;
         double g;
@@ -477,19 +498,19 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         double x[NCH];
 #pragma unroll
         for (int i = 0; i < NCH; ++i) x[i] = (kLanes * i + jbase < p) ? sm.ring[slot][i][tid] : 0.0;
-        double acc[KT];
+        double acc[KL];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+        for (int k = 0; k < KL; ++k) acc[k] = 0.0;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const double w = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+          for (int k = 0; k < KL; ++k) {
+            const double w = kReg ? Wr[i * KL + k] : Ws[(k * NCH + i) * kCT + tid];
             acc[k] += w * x[i];
           }
         }
-        const double tot = Halving<KT, 16>::run(acc, lane);
-        constexpr int kShift = 5 - ilog2(KT);
+        const double tot = Halving<KL, 16>::run(acc, lane);
+        constexpr int kShift = 5 - ilog2(KL);
         if ((lane & ((1 << kShift) - 1)) == 0) sm.red[fwarp][lane >> kShift] = tot;
         CLTRACE(6, fwarp == 0);
         bar_arrive_named(1);
@@ -505,15 +526,15 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         const double gw = sm.consts[tg & 1][0];
         const double step = gw * 1.0;
         const double thr = sm.consts[tg & 1][1];
-        double gch[KT];
+        double gch[KL];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) gch[k] = sm.gch[k];
+        for (int k = 0; k < KL; ++k) gch[k] = sm.gch[kbase + k];
         if (reset) {      // src/saga-dense.h:166-170
 #pragma unroll
           for (int i = 0; i < NCH; ++i)
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              if constexpr (kReg) Wr[i * KT + k] *= wscale;
+            for (int k = 0; k < KL; ++k) {
+              if constexpr (kReg) Wr[i * KL + k] *= wscale;
               else Ws[(k * NCH + i) * kCT + tid] *= wscale;
             }
         }
@@ -523,13 +544,13 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
         // beyond K hold zeros and stay zeros under these operations.
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          double w[KT], gs[KT], gnew[KT];
+          double w[KL], gs[KL], gnew[KL];
           double sq = 0.0;
           bool rare = false;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const double w_in = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
-            gs[k] = kReg ? Gr[i * KT + k] : Gs[(k * NCH + i) * kCT + tid];
+          for (int k = 0; k < KL; ++k) {
+            const double w_in = kReg ? Wr[i * KL + k] : Ws[(k * NCH + i) * kCT + tid];
+            gs[k] = kReg ? Gr[i * KL + k] : Gs[(k * NCH + i) * kCT + tid];
             const double gx = gch[k] * x[i];
             const double v = (w_in - gx * gw) - step * gs[k];
             w[k] = (PEN == kElasticNet) ? soft_threshold(v, thr) : v;
@@ -538,19 +559,19 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
           }
           if (__builtin_expect(rare, 0)) {
 #pragma unroll
-            for (int k = 0; k < KT; ++k) gnew[k] = gs[k] + (gch[k] * x[i]) / nd;
+            for (int k = 0; k < KL; ++k) gnew[k] = gs[k] + (gch[k] * x[i]) / nd;
           }
           if (PEN == kGroupLasso) {
             const double factor = bgs / sqrt(sq);
             const double mult = 1.0 - factor / ws_c;
 #pragma unroll
-            for (int k = 0; k < KT; ++k) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
+            for (int k = 0; k < KL; ++k) w[k] = (factor < 1.0) ? w[k] * mult : 0.0;
           }
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
+          for (int k = 0; k < KL; ++k) {
             if constexpr (kReg) {
-              Wr[i * KT + k] = w[k];
-              Gr[i * KT + k] = gnew[k];
+              Wr[i * KL + k] = w[k];
+              Gr[i * KL + k] = gnew[k];
             } else {
               Ws[(k * NCH + i) * kCT + tid] = w[k];
               Gs[(k * NCH + i) * kCT + tid] = gnew[k];
@@ -568,12 +589,12 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
       for (int i = 0; i < NCH; ++i) {
         const int j = kLanes * i + jbase;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          if (j < p && k < K) {
-            const size_t e = size_t(k) * p + j;
-            const double w_in = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
+        for (int k = 0; k < KL; ++k) {
+          if (j < p && kbase + k < K) {
+            const size_t e = size_t(kbase + k) * p + j;
+            const double w_in = kReg ? Wr[i * KL + k] : Ws[(k * NCH + i) * kCT + tid];
             const double w = w_in * wscale;
-            if constexpr (kReg) Wr[i * KT + k] = w;
+            if constexpr (kReg) Wr[i * KL + k] = w;
             else Ws[(k * NCH + i) * kCT + tid] = w;
             mc = fmax(mc, fabs(w - f.Wprev[e]));
             ms = fmax(ms, fabs(w));
@@ -630,10 +651,10 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
     for (int i = 0; i < NCH; ++i) {
       const int j = kLanes * i + jbase;
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        if (j < p && k < K) {
-          Wg[size_t(k) * p + j] = kReg ? Wr[i * KT + k] : Ws[(k * NCH + i) * kCT + tid];
-          Gg[size_t(k) * p + j] = kReg ? Gr[i * KT + k] : Gs[(k * NCH + i) * kCT + tid];
+      for (int k = 0; k < KL; ++k) {
+        if (j < p && kbase + k < K) {
+          Wg[size_t(kbase + k) * p + j] = kReg ? Wr[i * KL + k] : Ws[(k * NCH + i) * kCT + tid];
+          Gg[size_t(kbase + k) * p + j] = kReg ? Gr[i * KL + k] : Gs[(k * NCH + i) * kCT + tid];
         }
       }
     }
@@ -658,32 +679,38 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
   }
 }
 
-template <int KT, int NCH>
+template <int KT, int NCH, int CS>
 constexpr size_t cluster_smem(void) {
-  return sizeof(ClusterFixed<NCH>) + (cluster_reg_state(KT, NCH) ? 0 : sizeof(double) * 2 * size_t(KT) * NCH * kCT);
+  return sizeof(ClusterFixed<NCH>) + (cluster_reg_state(KT / CS, NCH) ? 0 : sizeof(double) * 2 * size_t(KT / CS) * NCH * kCT);
 }
 
 inline int nch_bucket(int p) {
   const int nch = (p + kLanes - 1) / kLanes;
   return nch <= 1 ? 1 : (nch <= 2 ? 2 : (nch <= 4 ? 4 : 0));
 }
-inline size_t fast_smem_bytes(int kt, int nch) {
+// class split of a shape (see the kernel): only with one slice, a separable prox and at least CS classes in the bucket
+inline int class_split(int kt, int p, int pen) {
+  if (p > 4 * kCT || pen == kGroupLasso) return 1;
+  const int cs = p <= 2 * kCT ? 4 : 2;
+  return kt >= cs ? cs : (kt >= 2 ? 2 : 1);
+}
+inline size_t fast_smem_bytes(int kt, int nch, int cs) {
   const size_t fixed = nch == 1 ? sizeof(ClusterFixed<1>) : (nch == 2 ? sizeof(ClusterFixed<2>) : sizeof(ClusterFixed<4>));
-  return fixed + (cluster_reg_state(kt, nch) ? 0 : sizeof(double) * 2 * size_t(kt) * nch * kCT);
+  return fixed + (cluster_reg_state(kt / cs, nch) ? 0 : sizeof(double) * 2 * size_t(kt / cs) * nch * kCT);
 }
 // the compile-time instantiations cover slice counts 1, 2, 4 whose state fits the registers or the shared memory
-inline bool fast_eligible(int K, int p) {
+inline bool fast_eligible(int K, int p, int pen) {
   const int nch = nch_bucket(p);
-  return nch != 0 && fast_smem_bytes(dense_kt_bucket(K), nch) <= dense_smem_budget();
+  return nch != 0 && fast_smem_bytes(dense_kt_bucket(K), nch, class_split(dense_kt_bucket(K), p, pen)) <= dense_smem_budget();
 }
 
-template <int KT, int PEN, int NCH>
+template <int KT, int PEN, int NCH, int CS>
 cudaError_t launch_cluster_variant(int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
-  constexpr size_t smem = cluster_smem<KT, NCH>();
+  constexpr size_t smem = cluster_smem<KT, NCH, CS>();
   if constexpr (smem > 227 * 1024) {
     return cudaErrorInvalidConfiguration;       // not reachable: fast_eligible() sends these shapes to the generic kernel
   } else {
-    cudaError_t e = cudaFuncSetAttribute(saga_dense_cluster_kernel<KT, PEN, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(saga_dense_cluster_kernel<KT, PEN, NCH, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nct, 1, 1);
@@ -697,44 +724,53 @@ cudaError_t launch_cluster_variant(int nct, FitDev* fit, Progress* prog, const R
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, saga_dense_cluster_kernel<KT, PEN, NCH>, fit, prog, ra);
+    return cudaLaunchKernelEx(&cfg, saga_dense_cluster_kernel<KT, PEN, NCH, CS>, fit, prog, ra);
   }
 }
 
 template <int KT, int PEN>
-cudaError_t launch_cluster_nch(int nch, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+cudaError_t launch_cluster_nch(int nch, int cs, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+  if constexpr (PEN != kGroupLasso && KT >= 2) {
+    if (nch == 1 && cs == 2) return launch_cluster_variant<KT, PEN, 1, 2>(nct, fit, prog, ra, st);
+    if constexpr (KT >= 4) {
+      if (nch == 1 && cs == 4) return launch_cluster_variant<KT, PEN, 1, 4>(nct, fit, prog, ra, st);
+    }
+  }
   switch (nch) {
-    case 1: return launch_cluster_variant<KT, PEN, 1>(nct, fit, prog, ra, st);
-    case 2: return launch_cluster_variant<KT, PEN, 2>(nct, fit, prog, ra, st);
-    default: return launch_cluster_variant<KT, PEN, 4>(nct, fit, prog, ra, st);
+    case 1: return launch_cluster_variant<KT, PEN, 1, 1>(nct, fit, prog, ra, st);
+    case 2: return launch_cluster_variant<KT, PEN, 2, 1>(nct, fit, prog, ra, st);
+    default: return launch_cluster_variant<KT, PEN, 4, 1>(nct, fit, prog, ra, st);
   }
 }
 
 template <int KT>
-cudaError_t launch_cluster_kt(int pen, int nch, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
+cudaError_t launch_cluster_kt(int pen, int nch, int cs, int nct, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
   switch (pen) {
-    case kRidge: return launch_cluster_nch<KT, kRidge>(nch, nct, fit, prog, ra, st);
-    case kElasticNet: return launch_cluster_nch<KT, kElasticNet>(nch, nct, fit, prog, ra, st);
-    default: return launch_cluster_nch<KT, kGroupLasso>(nch, nct, fit, prog, ra, st);
+    case kRidge: return launch_cluster_nch<KT, kRidge>(nch, cs, nct, fit, prog, ra, st);
+    case kElasticNet: return launch_cluster_nch<KT, kElasticNet>(nch, cs, nct, fit, prog, ra, st);
+    default: return launch_cluster_nch<KT, kGroupLasso>(nch, cs, nct, fit, prog, ra, st);
   }
 }
 
 }  // namespace
 
-size_t dense_cluster_smem_bytes(int K, int p) {
-  return fast_eligible(K, p) ? fast_smem_bytes(dense_kt_bucket(K), nch_bucket(p)) : dense_cluster_generic_smem_bytes(K, p);
+size_t dense_cluster_smem_bytes(int K, int p, int pen) {
+  const int kt = dense_kt_bucket(K);
+  return fast_eligible(K, p, pen) ? fast_smem_bytes(kt, nch_bucket(p), class_split(kt, p, pen)) : dense_cluster_generic_smem_bytes(K, p);
 }
 
 cudaError_t launch_saga_dense_cluster(int K, int p, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st) {
-  if (!fast_eligible(K, p)) return launch_saga_dense_cluster_generic(K, pen, smem, fit, prog, ra, st);
+  if (!fast_eligible(K, p, pen)) return launch_saga_dense_cluster_generic(K, pen, smem, fit, prog, ra, st);
   const int nch = nch_bucket(p);
-  const int nct = p <= 2 * kCT ? 2 : (p <= 4 * kCT ? 4 : kCluster);     // CTAs that own features; absent blocks are exact zeros
+  const int cs = class_split(dense_kt_bucket(K), p, pen);
+  // CTAs: one per 256-feature block of the design (absent blocks are exact zeros) x class split
+  const int nct = (p <= 2 * kCT ? 2 : (p <= 4 * kCT ? 4 : kCluster)) * cs;
   switch (dense_kt_bucket(K)) {
-    case 1: return launch_cluster_kt<1>(pen, nch, nct, fit, prog, ra, st);
-    case 4: return launch_cluster_kt<4>(pen, nch, nct, fit, prog, ra, st);
-    case 8: return launch_cluster_kt<8>(pen, nch, nct, fit, prog, ra, st);
-    case 16: return launch_cluster_kt<16>(pen, nch, nct, fit, prog, ra, st);
-    default: return launch_cluster_kt<32>(pen, nch, nct, fit, prog, ra, st);
+    case 1: return launch_cluster_kt<1>(pen, nch, cs, nct, fit, prog, ra, st);
+    case 4: return launch_cluster_kt<4>(pen, nch, cs, nct, fit, prog, ra, st);
+    case 8: return launch_cluster_kt<8>(pen, nch, cs, nct, fit, prog, ra, st);
+    case 16: return launch_cluster_kt<16>(pen, nch, cs, nct, fit, prog, ra, st);
+    default: return launch_cluster_kt<32>(pen, nch, cs, nct, fit, prog, ra, st);
   }
 }
 

@@ -133,3 +133,49 @@ def test_lazy_virtual_centring_does_not_preserve_the_reference_bits():
     differ = np.mean(eager != lazy)
     assert differ > 0.5                                     # most elements end with different bits
     np.testing.assert_allclose(lazy, eager, rtol=0, atol=1e-13)    # while agreeing to rounding level
+
+
+def test_recursive_halving_equals_the_xor_butterfly():
+    """saga_dense_cluster.cu reduces the K class sums of a warp by recursive halving: at offset o = 16, 8, ... a lane keeps
+    one half of its values and hands the other half to lane ^ o, so a level moves K/2, K/4, ... values instead of K. Every
+    pair sum a_i + a_(i^o) is still formed exactly once (by one of the two partners; addition commutes), so lane
+    (k << (5 - log2 K)) must end with the bits the plain 32-lane xor-butterfly of class k ends with (sgdnet_arith.h
+    item 2), for every power-of-two K <= 32."""
+    rng = np.random.default_rng(3)
+
+    def butterfly(v):                       # v: [32] values of one class, one per lane
+        v = np.array(v, dtype=np.float64)
+        for o in (16, 8, 4, 2, 1):
+            v = v + v[np.arange(32) ^ o]
+        return v
+
+    def halving(vals):                      # vals: [32 lanes][K]
+        lanes = np.arange(32)
+        cur = [np.array(vals[:, k]) for k in range(vals.shape[1])]       # cur[i][lane]
+        o = 16
+        while o > 0:
+            n = len(cur)
+            if n == 1:
+                cur = [cur[0] + cur[0][lanes ^ o]]
+            else:
+                up = (lanes & o) != 0
+                h = n // 2
+                nxt = []
+                for i in range(h):
+                    keep = np.where(up, cur[h + i], cur[i])
+                    send = np.where(up, cur[i], cur[h + i])
+                    nxt.append(keep + send[lanes ^ o])
+                cur = nxt
+            o //= 2
+        return cur[0]                       # lane L holds the total of class L >> (5 - log2 K)
+
+    for K in (1, 2, 4, 8, 16, 32):
+        shift = 5 - int(np.log2(K))
+        for trial in range(20):
+            vals = rng.normal(size=(32, K)) * 10.0 ** rng.integers(-6, 6, size=(32, K))
+            got = halving(vals)
+            for k in range(K):
+                ref = butterfly(vals[:, k])
+                assert np.all(ref == ref[0])
+                lanes_of_k = [L for L in range(32) if (L >> shift) == k]
+                assert all(got[L] == ref[0] for L in lanes_of_k), (K, k)
