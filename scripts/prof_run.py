@@ -1,5 +1,6 @@
-"""Short workloads for ncu captures (profiles/): python scripts/prof_run.py sparse|dense3|dense4 [epochs]
-sparse: config 2 (1M x 100k): `epochs` SAGA epochs at lambda[30] + 3 deviance passes through the stepping interface."""
+"""Short workloads for ncu captures (profiles/): python scripts/prof_run.py sparse|dense3|dense4|score [epochs]
+sparse: config 2 (1M x 100k): `epochs` SAGA epochs at lambda[30] + 3 deviance passes through the stepping interface.
+score: held-out scoring of a cv fold of config 5 (50k rows x 50k, 50 nnz/row, 100 lambdas): predict_score_kernel."""
 import ctypes as C
 import os
 import sys
@@ -17,6 +18,18 @@ epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 lib = sg.product() if not os.environ.get("SGDNET_VARIANT") else _abi.Library(os.path.join(ROOT, "sgdnet_b200", "libsgdnet_b200_" + os.environ["SGDNET_VARIANT"] + ".so"), "sgdnet_")
 ms = C.c_float(0)
 sess = C.c_void_p()
+if what == "score":
+    import time
+    x, y = synth.binomial_sparse(50_000, 50_000, 50, seed=1005)
+    L, p = 100, 50_000
+    g = np.random.default_rng(1)
+    beta = (g.normal(size=(L, p, 1)) * (g.uniform(size=(L, p, 1)) < np.linspace(0.001, 0.2, L)[:, None, None])).astype(np.float64)
+    a0 = g.normal(size=(L, 1))
+    for _ in range(2):
+        t0 = time.perf_counter()
+        sc = lib.score_deviance(x, y, 1, a0, beta)
+        print(f"score: 50000 x 50000, 50 nnz/row, {L} lambdas: {1e3 * (time.perf_counter() - t0):.1f} ms per call (host buffers in), dev[0]={sc[0]:.6f}")
+    sys.exit(0)
 if what == "sparse":
     x, y = synth.binomial_sparse(1_000_000, 100_000, 100, seed=1002)
     m = _abi.CscMatrix.from_any(x)
