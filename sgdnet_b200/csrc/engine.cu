@@ -939,6 +939,13 @@ struct Engine {
         }
         // Idle: decide the fit's next launch from its published progress
         const Progress pg = *j.mirror;
+        // A launch whose indices and conflict codes were prepared ahead is submitted only once that preparation has
+        // finished (host-side query). Waiting for it inside the stream instead (cudaStreamWaitEvent) would park a blocked
+        // wait at the head of one of the 32 hardware queues the batch's streams share, and every other fit's kernels
+        // queued behind it would stall with it.
+        if (jobs.size() > 1 && j.prepped && pg.status == kRunning && !(j.needs_finish || pg.status == kLambdaDone) &&
+            cudaEventQuery(j.ev_prep) == cudaErrorNotReady)
+          continue;
         progressed = true;
         if (pg.status == kFitDone) {
           if (score && j.test_rows && j.n_test > 0 && !j.scored) submit_score(j);

@@ -179,6 +179,25 @@ def test_user_lambda_order_and_debug_losses(cuda, oracle):
         rel_close(lg, lr, what="debug losses")
 
 
+@pytest.mark.parametrize("nnz_row", [12, 150])
+def test_sparse_debug_losses_and_deviance_through_the_tile_pass(cuda, oracle, nnz_row):
+    """The bulk-copy tile form of the loss pass (sparse, K = 1): per-epoch debug losses (mode 1) and per-lambda deviances
+    (mode 0, with the nonzero bitmap) against the oracle; 12 nonzeros per row stages every tile, 150 per row overflows
+    the stage (the tiles are read in place); n is not a multiple of the 32-row tile and some rows are empty."""
+    rng = np.random.default_rng(31)
+    n, p = 1000 + 13, 900
+    x = sp.random(n, p, density=nnz_row / p, random_state=11, format="lil")
+    x[7, :] = 0
+    x[n - 1, :] = 0
+    x = sp.csc_matrix(x)
+    y = (rng.uniform(size=n) < 0.4).astype(float)
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=1.0, standardize=False, nlambda=5, maxit=6, thresh=0.0, seed=12, debug=True)
+    assert_fit_parity(g.raw, r.raw)
+    assert len(g.diagnostics["loss"]) == len(r.diagnostics["loss"]) > 0
+    for lg, lr in zip(g.diagnostics["loss"], r.diagnostics["loss"]):
+        rel_close(lg, lr, what="debug losses")
+
+
 def test_rng_stream_is_advanced_exactly(cuda, oracle):
     """The generator handed back has consumed n * npasses draws: a second fit continues the same stream."""
     x, y = synth.random_data(200, 4, "gaussian", True, density=1.0, seed=3)
