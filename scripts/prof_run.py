@@ -63,5 +63,11 @@ d = []
 for _ in range(3):
     lib.check(lib.sym("session_finish_lambda")(sess, 30, C.byref(ms)), "finish")
     d.append(ms.value)
+d2 = []
+if what == "sparse":      # the state a warm-started lasso path sees: a few epochs at a strong penalty zero most weights
+    lib.check(lib.sym("session_run_epochs")(sess, 3, 3, C.byref(rng), C.byref(ms)), "run")
+    for _ in range(3):
+        lib.check(lib.sym("session_finish_lambda")(sess, 3, C.byref(ms)), "finish")
+        d2.append(ms.value)
 lib.sym("session_destroy")(sess)
-print(f"{what}: n={n} p={p} epoch ms {t} deviance pass ms {d}")
+print(f"{what}: n={n} p={p} epoch ms {t} deviance pass ms {d} (all weights live) {d2} (lasso-sparse weights)")
