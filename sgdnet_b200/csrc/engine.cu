@@ -727,8 +727,10 @@ struct Engine {
   int deps_ctas() const {
     int active = 0;
     for (const FitJob& j : jobs) active += (j.phase != Phase::Done && j.phase != Phase::Parked) ? 1 : 0;
+    if (deps_ctas_env > 0) return deps_ctas_env;
     return std::max(8, sms * 6 / std::max(1, active));
   }
+  int deps_ctas_env = std::getenv("SGDNET_DEPS_CTAS") ? std::atoi(std::getenv("SGDNET_DEPS_CTAS")) : 0;   // measurement aid
 
   // the caller's generator -> device, at the start of run(); a launch prepared ahead stays valid when the caller hands
   // back the generator exactly as it received it

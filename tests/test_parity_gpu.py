@@ -376,3 +376,20 @@ def test_edge_shapes(cuda, oracle):
     assert_fit_parity(g.raw, r.raw)
     g, r = both(cuda, oracle, xw, np.arange(25) % 3, family="multinomial", alpha=0.5, nlambda=5, maxit=30, seed=4)
     assert_fit_parity(g.raw, r.raw)
+
+
+def test_sparse_very_wide_design_without_the_nonzero_bitmap(cuda, oracle):
+    """p = 1.9 M features: the nonzero-coefficient bitmap (238 KB) no longer fits beside the tile ring of the deviance
+    pass, which then gathers every weight; the coefficient records (61 MB) spill the solver's L2 working set."""
+    rng = np.random.default_rng(41)
+    n, p, nnz_row = 600, 1_900_000, 20
+    cols = rng.integers(0, p, size=(n, nnz_row))
+    cols[:, :3] = rng.integers(0, 40, size=(n, 3))          # a few shared features so that rows conflict and a signal exists
+    rows = np.repeat(np.arange(n), nnz_row)
+    x = sp.csc_matrix((rng.uniform(0.5, 1.5, size=n * nnz_row), (rows, cols.ravel())), shape=(n, p))
+    x.sum_duplicates()
+    beta = np.zeros(40)
+    beta[:6] = [2.0, -2.0, 1.5, -1.5, 1.0, -1.0]
+    y = (np.asarray(x[:, :40] @ beta).ravel() + 0.3 * rng.normal(size=n) > 0).astype(float)
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=1.0, standardize=False, nlambda=4, maxit=8, thresh=1e-3, seed=14)
+    assert_fit_parity(g.raw, r.raw)
