@@ -1,28 +1,30 @@
 // saga_dense_cluster.cu — dense SAGA epochs on a thread-block cluster (reference: src/saga-dense.h:147-212), for
 // designs with p >= SGD_WIDE_P features (BASELINE configs 3 and 4).
 //
-// One cluster of 8 CTAs per fit; a CTA is 8 feature warps (256 lanes) + 1 control warp. Feature lane L = 256 * cta + tid
-// owns the features j = L, L + 2048, ... for ALL classes. Their W and g_sum stay in that lane's REGISTERS for the whole
-// launch when slices x classes <= 16 (configs 3 and 4), otherwise in the CTA's shared memory; nobody else touches
-// them, so the dense sweeps of the reference's update (the K x p matrix-vector product, the coefficient step, the prox
-// over all p features and the g_sum update, src/saga-dense.h:154, 176-183) are split 2048 ways. What crosses threads
-// per update is the K partial dot products, with the association of include/sgdnet_arith.h item 2 (= the oracle's
-// dot_dense_wide):
+// One cluster per fit: one CTA per 256-feature block of the design (2, 4 or 8 of them; blocks a narrow design does not
+// have are exact zeros in the specified sum and are simply absent), times the class split described at the kernel. A CTA
+// is 8 feature warps (256 lanes) + 1 control warp. Feature lane L = 256 * block + tid owns the features j = L, L + 2048,
+// ... for the CTA's classes. Their W and g_sum stay in that lane's REGISTERS for the whole launch when slices x classes
+// <= 16 (configs 3 and 4), otherwise in the CTA's shared memory; nobody else touches them, so the dense sweeps of the
+// reference's update (the K x p matrix-vector product, the coefficient step, the prox over all p features and the
+// g_sum update, src/saga-dense.h:154, 176-183) are split over up to 2048 lanes. What crosses threads per update is the
+// K partial dot products, with the association of include/sgdnet_arith.h item 2 (= the oracle's dot_dense_wide):
 //   lane: running sum over its features (ascending j)
 //   warp: the xor-butterfly 16, 8, 4, 2, 1 - computed by recursive halving: at offset o a lane keeps one half of its
 //         class sums and hands the other half to lane ^ o, so a level moves K/2, K/4, ... values instead of K (the
 //         SHFL unit, one warp-instruction per cycle per SM, is what bounded the plain butterfly); each pair sum
-//         a_i + a_(i^o) is formed once, by either partner - same operands, same bits
+//         a_i + a_(i^o) is formed once, by either partner - same operands, same bits (tests/test_arith_cpu.py)
 //   CTA:  the 8 warp sums added in ascending order by the control warp (class k in lane k)
-//   cluster: the 8 CTA sums exchanged all-to-all through DISTRIBUTED SHARED MEMORY - st.async into the other CTAs'
+//   cluster: the CTA sums exchanged all-to-all through DISTRIBUTED SHARED MEMORY - st.async into the other CTAs'
 //         shared memory, completing bytes on their mbarrier, so data and signal travel together and neither side
-//         fences - and added in ascending order by every control warp, which then runs the K-value gradient step
-//         redundantly: no second exchange. CTA 0 alone reads and writes the gradient memory; its value rides along.
+//         fences; the (class, destination) pairs are spread over the control warp's lanes - and added in ascending
+//         block order by every control warp, which then runs the K-value gradient step redundantly: no second
+//         exchange. CTA 0 alone reads and writes the gradient memory; its value rides along.
 // Inside a CTA the two hand-overs per update are named barriers used one way (bar.arrive by the producer side,
 // bar.sync by the consumer side): the feature warps never wait for "warp sums taken", the control warp never waits
 // for "g_change taken". Everything that is not on the path warp sums -> g_change (intercept step, gradient-memory
-// store, next sample's operands, the next row's bulk copies, the step constants' three divisions) runs in the
-// slack of the side that is waiting anyway.
+// store, next sample's operands, the next row's bulk copies, the step constants' two divisions) runs in the slack of
+// the control warp; the probe of the next row's mbarrier runs in the slack of the feature warps.
 // A CTA streams only ITS 256-feature slices of each sampled row: 1-D bulk copies (cp.async.bulk -> UBLKCP) into an
 // 8-deep shared-memory ring driven by the sampling sequence.
 // Algorithmic HBM bytes per update: 8*p (row) + 4 (index) + 8*K_y (y) + 16*K (gradient memory read + write).
