@@ -391,7 +391,6 @@ saga_dense_cluster_kernel(FitDev* __restrict__ fit, Progress* __restrict__ prog,
     a_pbar = smem_u32(&sm.pbar[0]);
   }
   constexpr uint32_t kParStride = (kCluster + 1) * 32 * 8;                 // bytes between the two parities of part[]
-  constexpr uint32_t kGmOffset = (kCluster * 32) * 8;                      // part[.][kCluster][lane] - part[.][0][lane]
 
   for (int ep = 0; ep < ra.n_epochs && !finished; ++ep) {
     if (control) {

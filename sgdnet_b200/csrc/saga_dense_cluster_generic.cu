@@ -72,11 +72,6 @@ __device__ __forceinline__ void wait_cluster(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ double ldcg_f64(const double* p) {
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 
 
 struct ClusterSmem {

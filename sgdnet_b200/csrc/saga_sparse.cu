@@ -155,6 +155,7 @@ __device__ __forceinline__ void ld_state(const FeatState* p, double& w, double& 
   w = __longlong_as_double(static_cast<long long>(a));
   g = __longlong_as_double(static_cast<long long>(b));
   lag = static_cast<uint32_t>(c);
+  (void)d;      // the record's padding word
 }
 __device__ __forceinline__ void st_state(FeatState* p, double w, double g, uint32_t lag) {
   asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(__double_as_longlong(w)), "l"(__double_as_longlong(g)),
@@ -183,7 +184,7 @@ __device__ __forceinline__ void wait_row_relaxed(uint64_t* ring, uint32_t q) {
 constexpr uint32_t kCodeGlobal = 1u << 11;
 
 constexpr int kDepSlots = 32;       // row instances staged per block iteration: the `window` rows before the block's rows + its own
-constexpr int kDepMaxWindow = 15;   // distances are 4-bit
+static_assert(kDepSlots <= 32, "one bit per staged row; distances are 4-bit (window <= 15)");
 constexpr int kDepBuckets = 8192;   // hashed feature buckets; a bucket holds one bit per staged row
 __device__ __forceinline__ uint32_t dep_hash1(int32_t j) { return (static_cast<uint32_t>(j) * 2654435761u) >> 19; }   // 13 bits
 __device__ __forceinline__ uint32_t dep_hash2(int32_t j) { return (static_cast<uint32_t>(j) * 0x85ebca6bu + 0x27d4eb2fu) >> 19; }
