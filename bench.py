@@ -133,10 +133,10 @@ def make_workload(n, p):
     return x, y
 
 
-def control_for(lib, n_lambda=100, lambda_=None, maxit=1000):
+def control_for(lib, n_lambda=100, lambda_=None, maxit=1000, standardize=False):
     from sgdnet_b200 import api
     return api.build_control("binomial", 1, alpha=1.0, nlambda=n_lambda, lambda_min_ratio=1e-4, lambda_=lambda_,
-                             maxit=maxit, standardize=False, intercept=True, thresh=1e-3, standardize_response=False,
+                             maxit=maxit, standardize=standardize, intercept=True, thresh=1e-3, standardize_response=False,
                              debug=False)
 
 
@@ -157,11 +157,11 @@ def cpu_arms():
     return arms
 
 
-def time_cpu_epochs(lib, x, y, lam, first, last):
+def time_cpu_epochs(lib, x, y, lam, first, last, standardize=False):
     """solver seconds of epochs first+1 .. last of a `last`-epoch fit at one lambda (same seed: the shorter fit is a
     prefix of the longer one)."""
     def run(epochs):
-        ctl, keep = control_for(lib, 1, [lam], maxit=epochs)
+        ctl, keep = control_for(lib, 1, [lam], maxit=epochs, standardize=standardize)
         ctl.tol = 0.0                                   # never converge early: exactly `epochs` epochs
         t0 = time.time()
         raw = lib.fit(x, y.reshape(-1, 1), ctl, lib.rng_from_seed(1))
@@ -322,6 +322,35 @@ def part_dense(lib):
                      "kernel": "saga_dense_cluster_kernel (thread-block cluster, one per fit)",
                      "cycles_per_update_at_1965MHz": t / n * 1.965e9}
         del x, xa
+    # sparse + standardize = TRUE (virtual centring: the reference's O(p) sweeps per update, saga_sparse_generic_kernel) at
+    # reduced p, against the oracle's portable restatement on one host core
+    x, y = synth.binomial_sparse(20_000, 2000, 16, seed=1012)
+    m = _abi.CscMatrix.from_any(x)
+    n, p = m.shape
+    ya = np.ascontiguousarray(y.reshape(-1, 1))
+    ctl, keep = api.build_control("binomial", 1, alpha=1.0, nlambda=100, lambda_min_ratio=1e-4, lambda_=None, maxit=1000, standardize=True,
+                                  intercept=True, thresh=1e-3, standardize_response=False, debug=False)
+    sess = C.c_void_p()
+    lib.check(lib.sym("session_create_sparse")(_abi._ptr(m.i, _abi.c_int32_p), _abi._ptr(m.p, _abi.c_int32_p), _abi._ptr(m.x, _abi.c_double_p),
+                                               C.c_int64(n), C.c_int64(p), _abi._ptr(ya, _abi.c_double_p), C.c_int32(1), C.byref(ctl),
+                                               C.byref(sess)), "session_create_sparse")
+    rng = lib.rng_from_seed(1)
+    ms = C.c_float(0)
+    times = []
+    for _ in range(3):
+        lib.check(lib.sym("session_run_epochs")(sess, 30, 1, C.byref(rng), C.byref(ms)), "run_epochs")
+        times.append(ms.value)
+    lib.sym("session_destroy")(sess)
+    t = min(times[1:]) * 1e-3
+    out["config2_standardized_sparse_20000x2000"] = {"updates_per_s": n / t, "epoch_ms": t * 1e3, "kernel": "saga_sparse_generic_kernel (one CTA; "
+                                                     "virtual centring touches all p coefficients on every update, as in the reference)"}
+    try:
+        from oracle_lib import load_oracle
+        lam = path_lambda(x, y, 30)
+        cpu_s, _, _ = time_cpu_epochs(load_oracle(), x, y, lam, 1, 3, standardize=True)
+        out["config2_standardized_sparse_20000x2000"]["cpu_oracle_updates_per_s_one_core"] = n * 2 / cpu_s
+    except Exception as exc:      # noqa: BLE001
+        out["config2_standardized_sparse_20000x2000"]["cpu_oracle_error"] = str(exc)
     return out
 
 

@@ -9,7 +9,7 @@ cd sgdnet_b200/csrc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr"
 nvcc $FLAGS $EXTRA -c $FILE.cu -o ../../build/${FILE}_$NAME.o
 OBJS=""
-for f in saga_dense saga_dense_cluster saga_dense_cluster_generic saga_sparse passes rng setup host_setup engine; do
+for f in saga_dense saga_dense_cluster saga_dense_cluster_generic saga_sparse saga_sparse_centred passes rng setup host_setup engine; do
   if [ $f = $FILE ]; then OBJS="$OBJS ../../build/${FILE}_$NAME.o"; else OBJS="$OBJS ../../build/$f.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libsgdnet_b200_$NAME.so $OBJS -lcudart -ldl

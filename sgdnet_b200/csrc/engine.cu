@@ -172,10 +172,11 @@ struct RawInput {
   const int32_t* ci = nullptr;
   const double* cv = nullptr;
   int64_t n_entries = 0;
+  int64_t max_row_nnz = 0;
   const double* dense_cm = nullptr;
 };
 
-enum class Variant { Dense, SparseK1, SparseGeneric };
+enum class Variant { Dense, SparseK1, SparseCentred, SparseGeneric };
 enum class Phase { Idle, Solver, Finish, Parked, Done };
 
 // One fit of a batch = one asynchronous pipeline: its own stream, its own rounds
@@ -227,6 +228,7 @@ struct FitJob {
   bool stale_prep = false;            // a prepared launch was discarded; its kernels may still be running on st_prep
   nvtxRangeId_t nvtx_launch = 0, nvtx_lambda = 0;      // open NVTX ranges (one per solver launch, one per lambda)
   bool nvtx_lambda_open = false;
+  uint16_t* pos_scratch = nullptr;    // sparse + virtual centring: position maps when the state does not fit shared memory
   int loss_blocks = 1;
   int loss_tiles = 0;                 // > 0: CTAs of the bulk-copy tile form of the loss pass (sparse K == 1)
   int mask_words = 0;                 // sparse K == 1: words of the nonzero-coefficient bitmap (0: p too large for it)
@@ -258,6 +260,7 @@ struct Engine {
   bool trace_rounds = std::getenv("SGDNET_TRACE_ROUNDS") != nullptr;   // per-launch device times on stderr
   bool host_rng = std::getenv("SGDNET_HOST_RNG") != nullptr;           // draw MT indices on the host (development aid)
   bool no_overlap = std::getenv("SGDNET_NO_PREP_OVERLAP") != nullptr;  // prepare a launch only when it is due
+  bool no_centred = std::getenv("SGDNET_NO_CENTRED") != nullptr;         // sparse + standardize on the generic kernel (measurement aid)
   bool no_loss_tiles = std::getenv("SGDNET_NO_LOSS_TILES") != nullptr;   // loss pass without the bulk-copy tile form (measurement aid)
   double seconds_setup = 0.0;
   double t_begin = 0.0, t_run = 0.0;
@@ -344,6 +347,7 @@ struct Engine {
     CK(cudaMemcpyAsync(tot, totals, sizeof(tot), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     raw.n_entries = tot[0] + 4;
+    raw.max_row_nnz = tot[1];
     RowInfo* rows = arena.alloc<RowInfo>(static_cast<size_t>(raw.n), false);
     int32_t* ci = arena.alloc<int32_t>(static_cast<size_t>(raw.n_entries), false);
     double* cv = arena.alloc<double>(static_cast<size_t>(raw.n_entries), false);
@@ -534,7 +538,15 @@ struct Engine {
     f.gsi = arena.alloc<double>(K);
     f.gmem = arena.alloc<double>(size_t(d.n) * K);
     f.lag = arena.alloc<uint32_t>(p);
-    job.variant = !d.sparse ? Variant::Dense : ((K == 1 && !f.standardize) ? Variant::SparseK1 : Variant::SparseGeneric);
+    job.variant = !d.sparse ? Variant::Dense
+                            : ((K == 1 && !f.standardize) ? Variant::SparseK1
+                                                          : ((K == 1 && raw.max_row_nnz <= kCentCap && !no_centred) ? Variant::SparseCentred
+                                                                                                                    : Variant::SparseGeneric));
+    if (job.variant == Variant::SparseCentred) {
+      bool in_smem = false;
+      centred_smem_bytes(p, &in_smem);
+      job.pos_scratch = in_smem ? nullptr : arena.alloc<uint16_t>(size_t(2) * p);
+    }
     f.st = (job.variant == Variant::SparseK1) ? arena.alloc<FeatState>(p) : nullptr;
     f.lag_scaling = d.sparse ? arena.alloc<double>(size_t(d.n) + 1, false) : nullptr;
     f.gamma = arena.upload(pl.gamma);
@@ -809,6 +821,8 @@ struct Engine {
       CK(launch_saga_dense_cluster(j.dev.K, j.dev.p, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else if (j.variant == Variant::Dense)
       CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
+    else if (j.variant == Variant::SparseCentred)
+      CK(launch_saga_sparse_centred(j.dev.p, j.dev_ptr, j.prog_ptr, ra, j.pos_scratch, j.st));
     else
       CK(launch_saga_sparse(j.variant == Variant::SparseK1, j.dev_ptr, j.prog_ptr, ra, j.st));
     ++j.launches;

@@ -32,6 +32,11 @@ int dense_kt_bucket(int K);
 size_t dense_cluster_smem_bytes(int K, int p, int pen);
 cudaError_t launch_saga_dense_cluster(int K, int p, int pen, size_t smem, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
 cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const RoundArgs& ra, cudaStream_t st);
+// sparse, K == 1, virtual centring (standardize = TRUE), rows of at most kCentCap nonzeros: the owner-computes kernel
+// (saga_sparse_centred.cu). pos_global: 2 * p uint16 of scratch, used when the state does not fit shared memory.
+constexpr int kCentCap = 256;
+size_t centred_smem_bytes(int p, bool* state_in_smem);
+cudaError_t launch_saga_sparse_centred(int p, FitDev* fit, Progress* prog, const RoundArgs& ra, uint16_t* pos_global, cudaStream_t st);
 
 // Conflict codes of a staged sequence for the wavefront kernel (sparse K == 1); a function of the sequence alone, so it
 // runs ahead of the solver launch that consumes it (on the fit's second stream, while the previous launch solves).

@@ -393,3 +393,33 @@ def test_sparse_very_wide_design_without_the_nonzero_bitmap(cuda, oracle):
     y = (np.asarray(x[:, :40] @ beta).ravel() + 0.3 * rng.normal(size=n) > 0).astype(float)
     g, r = both(cuda, oracle, x, y, family="binomial", alpha=1.0, standardize=False, nlambda=4, maxit=8, thresh=1e-3, seed=14)
     assert_fit_parity(g.raw, r.raw)
+
+
+@pytest.mark.parametrize("family,alpha,intercept", [("binomial", 1.0, True), ("gaussian", 0.0, True), ("binomial", 0.4, False)])
+@pytest.mark.parametrize("p", [900, 9000])
+def test_sparse_standardized_owner_computes_kernel(cuda, oracle, family, alpha, intercept, p):
+    """Sparse input with standardize = TRUE, K = 1 (saga_sparse_centred.cu): virtual centring touches every coefficient on
+    every update. p = 900: state in shared memory; p = 9000: state in HBM. Ridge moves wscale (lag-scaling table, resets);
+    empty rows, repeated samples and an all-zero column are in."""
+    rng = np.random.default_rng(51)
+    n = 700
+    x = sp.random(n, p, density=14.0 / p, random_state=3, format="lil")
+    x[5, :] = 0
+    x[:, 7] = 0
+    x = sp.csc_matrix(x)
+    eta = np.asarray(x[:, :30] @ rng.normal(size=30)).ravel()
+    y = (eta + 0.3 * rng.normal(size=n) > 0).astype(float) if family == "binomial" else eta + 0.1 * rng.normal(size=n)
+    g, r = both(cuda, oracle, x, y, family=family, alpha=alpha, intercept=intercept, standardize=True, nlambda=6, thresh=1e-4,
+                maxit=40, seed=17)
+    assert_fit_parity(g.raw, r.raw)
+
+
+def test_sparse_standardized_long_rows_fall_back_to_the_generic_kernel(cuda, oracle):
+    """A row with more nonzeros than the owner-computes kernel stages (256) sends the fit to saga_sparse_generic_kernel."""
+    rng = np.random.default_rng(52)
+    x = sp.random(300, 400, density=0.05, random_state=5, format="lil")
+    x[11, :330] = rng.uniform(0.2, 1.0, size=330)
+    x = sp.csc_matrix(x)
+    y = (rng.uniform(size=300) < 0.5).astype(float)
+    g, r = both(cuda, oracle, x, y, family="binomial", alpha=0.7, standardize=True, nlambda=5, maxit=30, seed=18)
+    assert_fit_parity(g.raw, r.raw)
