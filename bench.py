@@ -322,7 +322,7 @@ def part_dense(lib):
                      "kernel": "saga_dense_cluster_kernel (thread-block cluster, one per fit)",
                      "cycles_per_update_at_1965MHz": t / n * 1.965e9}
         del x, xa
-    # sparse + standardize = TRUE (virtual centring: the reference's O(p) sweeps per update, saga_sparse_generic_kernel) at
+    # sparse + standardize = TRUE (virtual centring: the reference's O(p) sweeps per update, saga_sparse_centred.cu) at
     # reduced p, against the oracle's portable restatement on one host core
     x, y = synth.binomial_sparse(20_000, 2000, 16, seed=1012)
     m = _abi.CscMatrix.from_any(x)
@@ -342,8 +342,9 @@ def part_dense(lib):
         times.append(ms.value)
     lib.sym("session_destroy")(sess)
     t = min(times[1:]) * 1e-3
-    out["config2_standardized_sparse_20000x2000"] = {"updates_per_s": n / t, "epoch_ms": t * 1e3, "kernel": "saga_sparse_generic_kernel (one CTA; "
-                                                     "virtual centring touches all p coefficients on every update, as in the reference)"}
+    out["config2_standardized_sparse_20000x2000"] = {"updates_per_s": n / t, "epoch_ms": t * 1e3, "kernel": "saga_sparse_centred_kernel (one CTA, owner "
+                                                     "computes; virtual centring touches all p coefficients on every update, as in the reference)",
+                                                     "cycles_per_update_at_1965MHz": t / n * 1.965e9}
     try:
         from oracle_lib import load_oracle
         lam = path_lambda(x, y, 30)

@@ -821,8 +821,13 @@ struct Engine {
       CK(launch_saga_dense_cluster(j.dev.K, j.dev.p, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
     else if (j.variant == Variant::Dense)
       CK(launch_saga_dense(j.dev.K, j.dev.penalty, j.dense_smem, j.dev_ptr, j.prog_ptr, ra, j.st));
-    else if (j.variant == Variant::SparseCentred)
-      CK(launch_saga_sparse_centred(j.dev.p, j.dev_ptr, j.prog_ptr, ra, j.pos_scratch, j.st));
+    else if (j.variant == Variant::SparseCentred) {
+      // the instantiation for this lambda's penalty: r = 1 - alpha gamma == 1 (the lasso) keeps wscale at exactly 1
+      const int li = std::min<int>(pg.lambda_ind, static_cast<int>(j.plan.alpha.size()) - 1);
+      const bool ident = (1.0 - j.plan.alpha[li] * j.plan.gamma[li]) == 1.0;
+      const int mode = j.dev.penalty == kElasticNet ? (ident ? 0 : 1) : ((j.dev.penalty == kRidge && !ident) ? 2 : 3);
+      CK(launch_saga_sparse_centred(j.dev.p, mode, j.dev_ptr, j.prog_ptr, ra, j.pos_scratch, j.st));
+    }
     else
       CK(launch_saga_sparse(j.variant == Variant::SparseK1, j.dev_ptr, j.prog_ptr, ra, j.st));
     ++j.launches;

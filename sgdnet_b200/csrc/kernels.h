@@ -36,7 +36,8 @@ cudaError_t launch_saga_sparse(bool fast_k1, FitDev* fit, Progress* prog, const 
 // (saga_sparse_centred.cu). pos_global: 2 * p uint16 of scratch, used when the state does not fit shared memory.
 constexpr int kCentCap = 256;
 size_t centred_smem_bytes(int p, bool* state_in_smem);
-cudaError_t launch_saga_sparse_centred(int p, FitDev* fit, Progress* prog, const RoundArgs& ra, uint16_t* pos_global, cudaStream_t st);
+// mode: 0 elastic net with alpha * gamma == 0 on the whole path (the lasso), 1 elastic net, 2 ridge, 3 general
+cudaError_t launch_saga_sparse_centred(int p, int mode, FitDev* fit, Progress* prog, const RoundArgs& ra, uint16_t* pos_global, cudaStream_t st);
 
 // Conflict codes of a staged sequence for the wavefront kernel (sparse K == 1); a function of the sequence alone, so it
 // runs ahead of the solver launch that consumes it (on the fit's second stream, while the previous launch solves).
