@@ -150,12 +150,12 @@ struct __align__(128) WaveSmem {
 };
 
 __device__ __forceinline__ void ld_state(const FeatState* p, double& w, double& g, uint32_t& lag) {
-  unsigned long long a, b, c, d;
-  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+  unsigned long long a, b, c;
+  [[maybe_unused]] unsigned long long pad;      // the record's padding word
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(pad) : "l"(p) : "memory");
   w = __longlong_as_double(static_cast<long long>(a));
   g = __longlong_as_double(static_cast<long long>(b));
   lag = static_cast<uint32_t>(c);
-  (void)d;      // the record's padding word
 }
 __device__ __forceinline__ void st_state(FeatState* p, double w, double g, uint32_t lag) {
   asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(__double_as_longlong(w)), "l"(__double_as_longlong(g)),
