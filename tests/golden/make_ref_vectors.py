@@ -55,6 +55,10 @@ GENERATED = {
     # sparse + standardize = TRUE on genuinely sparse rows (16 of 2000 columns): the reference's O(p) virtual-centring
     # sweeps interleaved with the lagged updates (src/saga-sparse.h:127-128, 276-277)
     "c2std": lambda: synth.binomial_sparse(20000, 2000, 16, seed=1012),
+    # BASELINE configs 3 / 4 at their full WIDTH (p = 784 x 10 classes, p = 2000 x 4 responses) on few rows: dense designs
+    # wide enough (p >= 512) for the thread-block-cluster solver and its eight-block dot product
+    "c3wide": lambda: synth.multinomial_dense(300, 784, 10, seed=1003),
+    "c4wide": lambda: synth.mgaussian_dense(250, 2000, 4, seed=1004),
 }
 
 
@@ -94,6 +98,8 @@ CASES = {
     "fixed_c4mini_dense_mgaussian": ("c4mini", dict(family="mgaussian", alpha=1.0, nlambda=8, thresh=0.0, maxit=5, seed=1)),
     "fixed_sparse_multinomial_std": ("sparse_multinomial", dict(family="multinomial", alpha=0.5, standardize=True, nlambda=6, thresh=0.0, maxit=5, seed=9)),
     "fixed_c2std_sparse_binomial_enet_std": ("c2std", dict(family="binomial", alpha=0.5, standardize=True, nlambda=5, thresh=0.0, maxit=8, seed=1)),
+    "fixed_c3wide_dense_multinomial": ("c3wide", dict(family="multinomial", alpha=0.8, nlambda=5, thresh=0.0, maxit=4, seed=1)),
+    "fixed_c4wide_dense_mgaussian": ("c4wide", dict(family="mgaussian", alpha=1.0, nlambda=5, thresh=0.0, maxit=4, seed=1)),
     "fixed_sparse_gaussian_std_nointercept": ("sparse_gaussian", dict(family="gaussian", alpha=0.3, standardize=True, intercept=False, nlambda=6, thresh=0.0, maxit=5, seed=2)),
 }
 
