@@ -49,8 +49,10 @@ def inputs():
 
 BUNDLED = ("abalone", "heart", "wine", "student")   # already fixtures of their own; not stored twice
 
-# Inputs too large to commit: regenerated from their seed wherever the vectors are used (numpy's PCG64 streams are
-# stable); a checksum of the generated arrays is stored with the outputs and checked on load.
+# Designs too large to commit: x is regenerated from its seed wherever the vectors are used (numpy's PCG64 streams and
+# their normal / uniform transforms are stable); a checksum of the generated arrays is stored with the outputs and
+# checked on load. The response IS stored: a generator that forms y = X B + noise goes through a BLAS matrix product,
+# whose summation order - hence the last bits of y - depends on the machine it runs on.
 GENERATED = {
     # sparse + standardize = TRUE on genuinely sparse rows (16 of 2000 columns): the reference's O(p) virtual-centring
     # sweeps interleaved with the lagged updates (src/saga-sparse.h:127-128, 276-277)
@@ -63,10 +65,16 @@ GENERATED = {
 
 
 def checksum(x, y):
+    """Exact (integer, wrap-around) sums over the bit patterns: the same on every machine, unlike a floating-point sum or
+    dot product, whose association belongs to the BLAS / SIMD width of the box it runs on."""
     x = sp.csc_matrix(x)
     x.sort_indices()
-    return np.array([float(x.data.sum()), float(np.dot(x.data, np.arange(x.data.size) % 97)), float(x.indices.sum()),
-                     float(np.asarray(y, dtype=np.float64).sum())])
+    bits = np.ascontiguousarray(x.data, dtype=np.float64).view(np.uint64)
+    ybits = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(-1).view(np.uint64)
+    with np.errstate(over="ignore"):
+        return np.array([bits.sum(dtype=np.uint64), (bits * (np.arange(bits.size, dtype=np.uint64) % np.uint64(97) + np.uint64(1))).sum(dtype=np.uint64),
+                         np.uint64(int(x.indices.sum(dtype=np.int64))), ybits.sum(dtype=np.uint64)], dtype=np.uint64)
+
 
 CASES = {
     # BASELINE config 1 exactly (R defaults: standardize, intercept, thresh 1e-3, maxit 1000, set.seed(1))
@@ -111,6 +119,7 @@ def main():
     for key, gen in GENERATED.items():
         ins[key] = gen()
         store[f"in/{key}/checksum"] = checksum(*ins[key])
+        store[f"in/{key}/y"] = np.asarray(ins[key][1])
     for key, (x, y) in ins.items():
         if key in BUNDLED or key in GENERATED:
             continue

@@ -27,7 +27,8 @@ _GEN_CACHE = {}
 def case_input(key):
     if key in GENERATED:
         if key not in _GEN_CACHE:
-            x, y = GENERATED[key]()
+            x, _ = GENERATED[key]()          # the design from its seed; the response as stored (see make_ref_vectors.py)
+            y = _npz()[f"in/{key}/y"]
             np.testing.assert_array_equal(checksum(x, y), _npz()[f"in/{key}/checksum"],
                                           err_msg=f"generated input '{key}' is not the one the reference vectors were made from")
             _GEN_CACHE[key] = (x, y)
